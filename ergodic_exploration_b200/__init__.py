@@ -1,0 +1,19 @@
+"""ergodic_exploration_b200 -- B200-native (sm_100a) hot path of
+bostoncleek/ergodic_exploration: the receding-horizon ergodic controller step
+ErgodicControl::control() and the phi_k target-coefficient contraction.
+
+The arithmetic lives in hand-written CUDA behind a C ABI
+(include/ergodic_b200.h -> libergodic_b200.so).  This package is the thin
+Python host mirror used by the tests and the benchmark; the C++ drop-in
+adapter is include/ergodic_exploration_b200/.  No CPU fallback exists.
+"""
+from .capi import (EB_ERR_CUDA, EB_ERR_INVALID_ARGUMENT, EB_ERR_NO_DEVICE, EB_OK, MODEL_OMNI,
+                   MODEL_SIMPLE_CART, ErgodicB200Error)
+from .controller import (ErgodicControl, Gaussian, GridBounds, Omni, PhikPlan, SimpleCart, Target,
+                         fp64_peak)
+
+__all__ = [
+    "ErgodicControl", "Gaussian", "GridBounds", "Omni", "PhikPlan", "SimpleCart", "Target", "fp64_peak",
+    "ErgodicB200Error", "MODEL_OMNI", "MODEL_SIMPLE_CART", "EB_OK", "EB_ERR_CUDA",
+    "EB_ERR_INVALID_ARGUMENT", "EB_ERR_NO_DEVICE",
+]

@@ -1,0 +1,315 @@
+"""Host-side mirror of the reference's controller API over the C ABI.
+
+``ErgodicControl`` keeps the reference's method names and argument meaning
+(ergodic_control.hpp:90-134: control, optTraj, addStateMemory, timeStep,
+setTarget, configTarget) for a BATCH of B independent instances living on one
+GPU.  numpy arrays go through the ``_host`` entry points (copies + sync, the
+end-to-end path); torch CUDA tensors go through the ``_dev`` entry points on
+torch's current stream (device-resident path).  Every number is computed by
+the CUDA kernels in csrc/ -- this file only marshals pointers.
+
+Array convention: Armadillo column-major 3xN == numpy (N, 3); batched buffers
+are (B, N, 3) / (B, 3) / (B, K).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import MODEL_OMNI, MODEL_SIMPLE_CART, EbConfig, ErgodicB200Error, check
+
+try:  # torch is plumbing only (device memory, streams); optional for the host path
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+@dataclass
+class Gaussian:
+    """target.hpp:56-107 -- 2-D Gaussian with diagonal covariance"""
+
+    mu: Sequence[float]
+    sigmas: Sequence[float]
+
+
+@dataclass
+class Target:
+    """target.hpp:110-161 -- list of Gaussians (addGaussian / deleteGaussian)"""
+
+    gaussians: list = field(default_factory=list)
+
+    def addGaussian(self, g: Gaussian) -> None:
+        self.gaussians.append(g)
+
+    def deleteGaussian(self, idx: int) -> None:
+        del self.gaussians[idx]
+
+
+class SimpleCart:
+    """models/cart.hpp:152-206"""
+
+    model_id = MODEL_SIMPLE_CART
+    state_space = 3
+
+
+class Omni:
+    """models/omni.hpp:164-215"""
+
+    model_id = MODEL_OMNI
+    state_space = 3
+
+
+@dataclass
+class GridBounds:
+    """The only part of GridMap the controller reads (grid.hpp:214-235)."""
+
+    xmin: float
+    xmax: float
+    ymin: float
+    ymax: float
+
+    def as_tuple(self):
+        return (float(self.xmin), float(self.xmax), float(self.ymin), float(self.ymax))
+
+
+def _is_cuda_tensor(a) -> bool:
+    return torch is not None and isinstance(a, torch.Tensor) and a.is_cuda
+
+
+def _np_f64(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+class ErgodicControl:
+    """Batched drop-in for ErgodicControl<ModelT> (ergodic_control.hpp:72-185)."""
+
+    def __init__(self, model, dt: float, horizon: float, resolution: float, exploration_weight: float,
+                 num_basis: int, buffer_size: int, batch_size: int, Rinv, umin, umax, *, batch: int = 1,
+                 device: int = 0, seed: int = 0xE16C0D1C, barrier_weight: float = 25.0,
+                 barrier_eps: float = 0.05):
+        self._lib = capi.load()
+        cfg = EbConfig()
+        model_id = model if isinstance(model, int) else model.model_id
+        self._lib.eb_config_defaults(C.byref(cfg), model_id)
+        cfg.batch, cfg.device = int(batch), int(device)
+        cfg.dt, cfg.horizon, cfg.resolution = float(dt), float(horizon), float(resolution)
+        cfg.expl_weight = float(exploration_weight)
+        cfg.num_basis, cfg.buffer_size, cfg.batch_size = int(num_basis), int(buffer_size), int(batch_size)
+        R = _np_f64(Rinv, (3, 3))
+        for r in range(3):
+            for c in range(3):
+                cfg.Rinv[r + 3 * c] = R[r, c]  # column-major
+        for i in range(3):
+            cfg.umin[i] = float(umin[i])
+            cfg.umax[i] = float(umax[i])
+        cfg.barrier_weight, cfg.barrier_eps, cfg.seed = float(barrier_weight), float(barrier_eps), int(seed)
+        h = C.c_void_p()
+        st = self._lib.eb_create(C.byref(cfg), C.byref(h))
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(self._lib.eb_last_error().decode())  # std::invalid_argument in the reference
+        check(st)
+        self._h = h
+        self.cfg = cfg
+        self.batch = int(batch)
+        self.device = int(device)
+        self.steps = self._lib.eb_steps(h)
+        self.num_coeff = self._lib.eb_num_coeff(h)
+        self.batch_size = int(batch_size)
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.eb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clone(self) -> "ErgodicControl":
+        other = object.__new__(ErgodicControl)
+        other.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_h"})
+        h = C.c_void_p()
+        check(self._lib.eb_clone(self._h, C.byref(h)))
+        other._h = h
+        return other
+
+    def _sync_stream(self):
+        if torch is not None and torch.cuda.is_available():
+            s = torch.cuda.current_stream(self.device).cuda_stream
+            check(self._lib.eb_set_stream(self._h, C.c_void_p(s)))
+
+    # -- reference API ------------------------------------------------------
+    def timeStep(self) -> float:
+        return self._lib.eb_time_step(self._h)
+
+    def setTarget(self, target) -> None:
+        gs = target.gaussians if isinstance(target, Target) else list(target)
+        mu = _np_f64([g.mu for g in gs]).reshape(-1)
+        sg = _np_f64([g.sigmas for g in gs]).reshape(-1)
+        check(self._lib.eb_set_target_gaussians(self._h, len(gs), mu.ctypes.data, sg.ctypes.data))
+
+    def configTarget(self, grid) -> bool:
+        b = grid.as_tuple() if hasattr(grid, "as_tuple") else tuple(float(v) for v in grid)
+        self._sync_stream()
+        rebuilt = C.c_int(0)
+        check(self._lib.eb_config_target(self._h, *b, C.byref(rebuilt)))
+        return bool(rebuilt.value)
+
+    def addStateMemory(self, x) -> None:
+        if _is_cuda_tensor(x):
+            self._sync_stream()
+            assert x.dtype == torch.float64 and x.is_contiguous() and x.numel() == 3 * self.batch
+            check(self._lib.eb_add_state_memory_dev(self._h, C.c_void_p(x.data_ptr())))
+        else:
+            x = _np_f64(x).reshape(self.batch, 3)
+            check(self._lib.eb_add_state_memory_host(self._h, x.ctypes.data))
+
+    def control(self, grid, x, mem_idx=None, u0=None, metric=None):
+        """One control() iteration for all instances.  Returns u0 (B, 3); pass
+        ``metric`` (B,) to also receive sum_k lamda_k (c_k - phi_k)^2."""
+        b = grid.as_tuple() if hasattr(grid, "as_tuple") else tuple(float(v) for v in grid)
+        self._sync_stream()
+        if _is_cuda_tensor(x):
+            assert x.dtype == torch.float64 and x.is_contiguous() and x.numel() == 3 * self.batch
+            if u0 is None:
+                u0 = torch.empty((self.batch, 3), dtype=torch.float64, device=x.device)
+            idx_p = C.c_void_p(mem_idx.data_ptr()) if mem_idx is not None else None
+            met_p = C.c_void_p(metric.data_ptr()) if metric is not None else None
+            st = self._lib.eb_control_dev(self._h, *b, C.c_void_p(x.data_ptr()), idx_p,
+                                          C.c_void_p(u0.data_ptr()), met_p)
+        else:
+            x = _np_f64(x).reshape(self.batch, 3)
+            if u0 is None:
+                u0 = np.empty((self.batch, 3))
+            idx_p = None
+            if mem_idx is not None:
+                mem_idx = np.ascontiguousarray(mem_idx, dtype=np.int32)
+                idx_p = mem_idx.ctypes.data
+            met_p = metric.ctypes.data if metric is not None else None
+            st = self._lib.eb_control_host(self._h, *b, x.ctypes.data, idx_p, u0.ctypes.data, met_p)
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(self._lib.eb_last_error().decode())
+        check(st)
+        return u0
+
+    def check(self) -> None:
+        """Synchronise and surface device-side faults of earlier device-path calls."""
+        st = self._lib.eb_check_status(self._h)
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(self._lib.eb_last_error().decode())
+        check(st)
+
+    def optTraj(self, out=None):
+        self._sync_stream()
+        if _is_cuda_tensor(out):
+            check(self._lib.eb_opt_traj_dev(self._h, C.c_void_p(out.data_ptr())))
+            return out
+        xt = np.empty((self.batch, self.steps, 3))
+        st = self._lib.eb_opt_traj_host(self._h, xt.ctypes.data)
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(self._lib.eb_last_error().decode())
+        check(st)
+        return xt
+
+    # -- state access (checkpoint / teacher forcing) -------------------------
+    def get_ut(self) -> np.ndarray:
+        ut = np.empty((self.batch, self.steps, 3))
+        check(self._lib.eb_get_ut(self._h, ut.ctypes.data))
+        return ut
+
+    def set_ut(self, ut) -> None:
+        ut = _np_f64(ut).reshape(self.batch, self.steps, 3)
+        check(self._lib.eb_set_ut(self._h, ut.ctypes.data))
+
+    def get_ck(self) -> np.ndarray:
+        ck = np.empty((self.batch, self.num_coeff))
+        check(self._lib.eb_get_ck(self._h, ck.ctypes.data))
+        return ck
+
+    def get_phik(self):
+        ph = np.empty(self.num_coeff)
+        lx, ly = C.c_double(0), C.c_double(0)
+        check(self._lib.eb_get_phik(self._h, ph.ctypes.data, C.byref(lx), C.byref(ly)))
+        return ph, lx.value, ly.value
+
+    def set_phik(self, phik, lx: float, ly: float) -> None:
+        ph = _np_f64(phik).reshape(self.num_coeff)
+        check(self._lib.eb_set_phik(self._h, ph.ctypes.data, float(lx), float(ly)))
+
+    def memory_size(self) -> int:
+        return int(self._lib.eb_memory_size(self._h))
+
+    def last_mem_idx(self) -> Optional[np.ndarray]:
+        n = C.c_int(0)
+        idx = np.zeros((self.batch, self.batch_size), dtype=np.int32)
+        check(self._lib.eb_get_last_mem_idx(self._h, idx.ctypes.data, C.byref(n)))
+        return idx[:, : n.value] if n.value > 0 else None
+
+    def launch_count(self) -> int:
+        return int(self._lib.eb_launch_count(self._h))
+
+
+class PhikPlan:
+    """phi_k = (C_y^T Phi C_x) / sum(Phi) for a dense density on the
+    configTarget grid (Target::fill normalisation + Basis::spatialCoeff)."""
+
+    def __init__(self, nx: int, ny: int, resolution: float, lx: float, ly: float, nb: int, device: int = 0,
+                 algo: int = 0):
+        self._lib = capi.load()
+        h = C.c_void_p()
+        st = self._lib.eb_phik_plan_create(device, nx, ny, float(resolution), float(lx), float(ly), nb, C.byref(h))
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(self._lib.eb_last_error().decode())
+        check(st)
+        self._h, self.nx, self.ny, self.nb, self.device = h, nx, ny, nb, device
+        if algo:
+            check(self._lib.eb_phik_plan_set_algo(h, algo))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.eb_phik_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def execute(self, phi, phik=None, phi_sum=None):
+        if _is_cuda_tensor(phi):
+            s = torch.cuda.current_stream(self.device).cuda_stream
+            check(self._lib.eb_phik_plan_set_stream(self._h, C.c_void_p(s)))
+            assert phi.dtype == torch.float64 and phi.is_contiguous() and phi.numel() == self.nx * self.ny
+            if phik is None:
+                phik = torch.empty(self.nb * self.nb, dtype=torch.float64, device=phi.device)
+            sp = C.c_void_p(phi_sum.data_ptr()) if phi_sum is not None else None
+            check(self._lib.eb_phik_execute_dev(self._h, C.c_void_p(phi.data_ptr()), C.c_void_p(phik.data_ptr()), sp))
+            return phik
+        phi = _np_f64(phi).reshape(self.ny, self.nx)
+        out = np.empty(self.nb * self.nb)
+        s = C.c_double(0.0)
+        check(self._lib.eb_phik_execute_host(self._h, phi.ctypes.data, out.ctypes.data, C.byref(s)))
+        self.last_sum = s.value
+        return out
+
+    def launch_count(self) -> int:
+        return int(self._lib.eb_phik_launch_count(self._h))
+
+
+def fp64_peak(device: int = 0):
+    """Measured FP64 TFLOP/s of the device: (DFMA loop, DMMA loop)."""
+    lib = capi.load()
+    a, b = C.c_double(0), C.c_double(0)
+    check(lib.eb_fp64_peak(device, C.byref(a), C.byref(b)))
+    return a.value, b.value

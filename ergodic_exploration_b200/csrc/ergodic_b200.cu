@@ -1,0 +1,879 @@
+// ergodic_b200.cu -- C ABI (include/ergodic_b200.h) over the sm_100a kernels.
+//
+// Host-side state mirrors the private members of the reference's
+// ErgodicControl (ergodic_control.hpp:165-184), batched over B instances and
+// resident on the device: ut_ (ping-pong, 3 x N x B), pose_, phik_, the
+// replay buffer (time-major [cap][B][3]) and the Basis tables.
+// There is no CPU implementation behind this ABI: every entry point either
+// launches CUDA work or fails.
+#include "../../include/ergodic_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "phik_dmma.cuh"
+#include "phik_kernels.cuh"
+#include "solve_kernel.cuh"
+
+namespace
+{
+thread_local std::string g_err;
+
+eb_status fail(eb_status st, const std::string& msg)
+{
+  g_err = msg;
+  return st;
+}
+
+#define EB_CUDA(expr)                                                                                   \
+  do                                                                                                    \
+  {                                                                                                     \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+    {                                                                                                   \
+      const eb_status st__ = (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ||         \
+                              e__ == cudaErrorInvalidDevice) ?                                          \
+                                 EB_ERR_NO_DEVICE :                                                     \
+                                 EB_ERR_CUDA;                                                           \
+      return fail(st__, std::string(#expr) + ": " + cudaGetErrorName(e__) + ": " + cudaGetErrorString(e__)); \
+    }                                                                                                   \
+  } while (0)
+
+// grid.hpp:61-64
+unsigned axis_length(double lower, double upper, double resolution)
+{
+  return static_cast<unsigned>(std::round((upper - lower) / resolution));
+}
+
+// numerics.hpp:67-70
+bool almost_equal(double a, double b) { return std::fabs(a - b) < 1.0e-12; }
+
+// configTarget's accumulated grid coordinates (ergodic_control.hpp:394-407)
+std::vector<double> accumulated_axis(int n, double resolution)
+{
+  std::vector<double> v(n);
+  double x = 0.0;
+  for (int i = 0; i < n; i++)
+  {
+    v[i] = x;
+    x += resolution;
+  }
+  return v;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// phi_k plan
+// ---------------------------------------------------------------------------
+struct eb_phik_plan
+{
+  int device = 0, nx = 0, ny = 0, nb = 0, algo = 0;
+  double resolution = 0, lx = 0, ly = 0;
+  cudaStream_t stream = nullptr;
+  double *d_xs = nullptr, *d_ys = nullptr;  // grid coordinates
+  double *d_cx = nullptr, *d_cy = nullptr;  // cosine tables [n][32]
+  double *d_T = nullptr;                    // stage-1 result [ny][32]
+  double *d_parts = nullptr;                // partial 32x32 blocks
+  double *d_phik = nullptr, *d_sum = nullptr;  // staging for the _host call
+  int max_parts = 0;
+  long long launches = 0;
+};
+
+extern "C" {
+
+int eb_abi_version(void) { return EB_ABI_VERSION; }
+const char* eb_last_error(void) { return g_err.c_str(); }
+
+int eb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void eb_config_defaults(eb_config* cfg, int model)
+{
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->model = model;
+  cfg->batch = 1;
+  cfg->device = 0;
+  cfg->dt = 0.1;           // config/explore_*.yaml ec_dt
+  cfg->horizon = 5.0;      // ec_horizon
+  cfg->resolution = 0.1;   // target_resolution
+  cfg->expl_weight = 1.0;  // expl_weight
+  cfg->num_basis = 10;
+  cfg->buffer_size = 1000000;
+  cfg->batch_size = 100;
+  // Rinv = diag(1 / control_weights) (exploration_omni_node.cpp:161-164,
+  // exploration_cart_node.cpp:156-159)
+  cfg->Rinv[0] = 1.0;
+  cfg->Rinv[4] = model == EB_MODEL_OMNI ? 1.0 : 0.0;
+  cfg->Rinv[8] = 2.0;
+  cfg->umin[0] = -1.0;
+  cfg->umax[0] = 1.0;
+  cfg->umin[1] = model == EB_MODEL_OMNI ? -1.0 : 0.0;
+  cfg->umax[1] = model == EB_MODEL_OMNI ? 1.0 : 0.0;
+  cfg->umin[2] = -2.0;
+  cfg->umax[2] = 2.0;
+  cfg->barrier_weight = 25.0;  // ergodic_control.hpp:457
+  cfg->barrier_eps = 0.05;     // ergodic_control.hpp:458
+  cfg->seed = 0xE16C0D1Cull;
+}
+
+eb_status eb_phik_plan_create(int device, int nx, int ny, double resolution, double lx, double ly, int nb,
+                              eb_phik_plan** out)
+{
+  if (!out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create: out is NULL");
+  *out = nullptr;
+  if (nx < 1 || ny < 1 || nb < 1 || nb > 32)
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create: need nx, ny >= 1 and 1 <= nb <= 32");
+  if (!(lx > 0.0) || !(ly > 0.0) || !(resolution > 0.0))
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create: lx, ly, resolution must be positive");
+  EB_CUDA(cudaSetDevice(device));
+  eb_phik_plan* p = new (std::nothrow) eb_phik_plan();
+  if (!p) return fail(EB_ERR_CUDA, "out of host memory");
+  p->device = device;
+  p->nx = nx;
+  p->ny = ny;
+  p->nb = nb;
+  p->resolution = resolution;
+  p->lx = lx;
+  p->ly = ly;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  p->max_parts = std::max(1, sms);
+  const std::vector<double> xs = accumulated_axis(nx, resolution), ys = accumulated_axis(ny, resolution);
+  auto cleanup = [&](eb_status st) {
+    eb_phik_plan_destroy(p);
+    return st;
+  };
+#define EB_CUDA_P(expr)                                                                      \
+  do                                                                                         \
+  {                                                                                          \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return cleanup(fail(EB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__))); \
+  } while (0)
+  EB_CUDA_P(cudaMalloc(&p->d_xs, sizeof(double) * nx));
+  EB_CUDA_P(cudaMalloc(&p->d_ys, sizeof(double) * ny));
+  EB_CUDA_P(cudaMalloc(&p->d_cx, sizeof(double) * (size_t)nx * eb::kPhikLd));
+  EB_CUDA_P(cudaMalloc(&p->d_cy, sizeof(double) * (size_t)ny * eb::kPhikLd));
+  EB_CUDA_P(cudaMalloc(&p->d_T, sizeof(double) * (size_t)ny * eb::kPhikLd));
+  EB_CUDA_P(cudaMalloc(&p->d_parts, sizeof(double) * 1024 * (size_t)p->max_parts));
+  EB_CUDA_P(cudaMalloc(&p->d_phik, sizeof(double) * 1024));
+  EB_CUDA_P(cudaMalloc(&p->d_sum, sizeof(double)));
+  EB_CUDA_P(cudaMemcpy(p->d_xs, xs.data(), sizeof(double) * nx, cudaMemcpyHostToDevice));
+  EB_CUDA_P(cudaMemcpy(p->d_ys, ys.data(), sizeof(double) * ny, cudaMemcpyHostToDevice));
+  // basis.cpp:85: cos(k * (PI / l) * x)
+  eb::cos_table_kernel<<<(nx * eb::kPhikLd + 255) / 256, 256>>>(p->d_xs, nx, eb::kPi / lx, nb, p->d_cx);
+  eb::cos_table_kernel<<<(ny * eb::kPhikLd + 255) / 256, 256>>>(p->d_ys, ny, eb::kPi / ly, nb, p->d_cy);
+  p->launches += 2;
+  EB_CUDA_P(cudaGetLastError());
+  EB_CUDA_P(cudaDeviceSynchronize());
+#undef EB_CUDA_P
+  *out = p;
+  return EB_OK;
+}
+
+void eb_phik_plan_destroy(eb_phik_plan* p)
+{
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaFree(p->d_xs);
+  cudaFree(p->d_ys);
+  cudaFree(p->d_cx);
+  cudaFree(p->d_cy);
+  cudaFree(p->d_T);
+  cudaFree(p->d_parts);
+  cudaFree(p->d_phik);
+  cudaFree(p->d_sum);
+  delete p;
+}
+
+eb_status eb_phik_plan_set_stream(eb_phik_plan* p, void* s)
+{
+  if (!p) return fail(EB_ERR_INVALID_ARGUMENT, "plan is NULL");
+  p->stream = static_cast<cudaStream_t>(s);
+  return EB_OK;
+}
+
+eb_status eb_phik_plan_set_algo(eb_phik_plan* p, int algo)
+{
+  if (!p) return fail(EB_ERR_INVALID_ARGUMENT, "plan is NULL");
+  if (algo < 0 || algo > 2) return fail(EB_ERR_INVALID_ARGUMENT, "algo must be 0 (auto), 1 (simple) or 2 (dmma)");
+  if (algo == 2 && !eb::phik_dmma_supported(p->nx, p->ny))
+    return fail(EB_ERR_UNSUPPORTED, "the DMMA phi_k kernel needs nx % 4 == 0 and nx >= 128");
+  p->algo = algo;
+  return EB_OK;
+}
+
+long long eb_phik_launch_count(const eb_phik_plan* p) { return p ? p->launches : 0; }
+
+eb_status eb_phik_execute_dev(eb_phik_plan* p, const double* phi_dev, double* phik_dev, double* phi_sum_dev)
+{
+  if (!p || !phi_dev || !phik_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_execute_dev: NULL argument");
+  EB_CUDA(cudaSetDevice(p->device));
+  int algo = p->algo;
+  if (algo == 0) algo = (eb::phik_dmma_supported(p->nx, p->ny) && (long long)p->nx * p->ny >= (1 << 18)) ? 2 : 1;
+  int nparts = 1;
+  if (algo == 2)
+  {
+    nparts = eb::phik_dmma_launch(phi_dev, p->nx, p->ny, p->d_cx, p->d_cy, p->d_parts, p->max_parts, p->stream);
+    if (nparts < 0) return fail(EB_ERR_CUDA, std::string("phik_dmma_launch: ") + cudaGetErrorString(cudaGetLastError()));
+    p->launches += 1;
+  }
+  else
+  {
+    eb::phik_stage1_simple<<<p->ny, 256, 0, p->stream>>>(phi_dev, p->nx, p->d_cx, p->d_T);
+    eb::phik_stage2_simple<<<32, 256, 0, p->stream>>>(p->d_T, p->ny, p->d_cy, p->d_parts);
+    p->launches += 2;
+  }
+  eb::phik_finalize<<<1, 1024, 0, p->stream>>>(p->d_parts, nparts, p->nb, phik_dev, phi_sum_dev);
+  p->launches += 1;
+  EB_CUDA(cudaGetLastError());
+  return EB_OK;
+}
+
+eb_status eb_phik_execute_host(eb_phik_plan* p, const double* phi, double* phik, double* phi_sum)
+{
+  if (!p || !phi || !phik) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_execute_host: NULL argument");
+  EB_CUDA(cudaSetDevice(p->device));
+  double* d_phi = nullptr;
+  const size_t bytes = sizeof(double) * (size_t)p->nx * p->ny;
+  EB_CUDA(cudaMalloc(&d_phi, bytes));
+  cudaError_t e = cudaMemcpyAsync(d_phi, phi, bytes, cudaMemcpyHostToDevice, p->stream);
+  eb_status st = EB_OK;
+  if (e == cudaSuccess) st = eb_phik_execute_dev(p, d_phi, p->d_phik, p->d_sum);
+  if (e == cudaSuccess && st == EB_OK)
+    e = cudaMemcpyAsync(phik, p->d_phik, sizeof(double) * p->nb * p->nb, cudaMemcpyDeviceToHost, p->stream);
+  if (e == cudaSuccess && st == EB_OK && phi_sum)
+    e = cudaMemcpyAsync(phi_sum, p->d_sum, sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+  if (e == cudaSuccess && st == EB_OK) e = cudaStreamSynchronize(p->stream);
+  cudaFree(d_phi);
+  if (st != EB_OK) return st;
+  if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_phik_execute_host: ") + cudaGetErrorString(e));
+  return EB_OK;
+}
+
+eb_status eb_phik_from_grid_host(int device, const double* phi, int nx, int ny, double resolution, double lx,
+                                 double ly, int nb, double* phik, double* phi_sum)
+{
+  eb_phik_plan* p = nullptr;
+  eb_status st = eb_phik_plan_create(device, nx, ny, resolution, lx, ly, nb, &p);
+  if (st != EB_OK) return st;
+  st = eb_phik_execute_host(p, phi, phik, phi_sum);
+  eb_phik_plan_destroy(p);
+  return st;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// controller
+// ---------------------------------------------------------------------------
+struct eb_controller
+{
+  eb_config cfg{};
+  int N = 0, K = 0, nb = 0, B = 0;
+  cudaStream_t stream = nullptr;
+  double* d_ut[2] = { nullptr, nullptr };  // ping-pong control signal, [B][N][3]
+  int cur = 0;                             // d_ut[cur] is ut_
+  double* d_pose = nullptr;                // [B][3], pose_ of the last control()
+  double* d_hist = nullptr;                // replay buffer [cap][B][3]
+  long long hist_cap = 0, mem_count = 0;
+  double *d_phik = nullptr, *d_lamk = nullptr;
+  double *d_u0 = nullptr, *d_metric = nullptr, *d_ck = nullptr, *d_x = nullptr;
+  int *d_mem_idx_in = nullptr, *d_mem_idx_out = nullptr, *d_fault = nullptr;
+  int last_idx_count = 0;
+  double lx = 0.0, ly = 0.0;  // basis_.lx_, basis_.ly_ (0, 0 at construction :208)
+  double map_pos[2] = { 0.0, 0.0 };
+  std::vector<double> gauss_mu, gauss_sigma;  // target_
+  eb_phik_plan* plan = nullptr;               // cached for the current extent
+  double* d_phi_grid = nullptr;
+  size_t phi_grid_cells = 0;
+  double* d_gauss = nullptr;
+  int gauss_cap = 0;
+  unsigned long long call = 0;
+  long long launches = 0;
+  bool have_pose = false;
+};
+
+namespace
+{
+template <int MODEL, int NB>
+cudaError_t launch_solve_t(const eb::SolveParams& p, int rounds, cudaStream_t s)
+{
+  const size_t per_warp = sizeof(double) * (2 * NB * eb::kTabStride + eb::kRecFields * 32 * (size_t)rounds);
+  const size_t smem = sizeof(double) * 2 * NB * NB + eb::kSolveWarps * per_warp;
+  static size_t configured = 0;  // per instantiation
+  if (smem > configured)
+  {
+    cudaError_t e =
+        cudaFuncSetAttribute(eb::solve_kernel<MODEL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int grid = (p.B + eb::kSolveWarps - 1) / eb::kSolveWarps;
+  eb::solve_kernel<MODEL, NB><<<grid, eb::kSolveWarps * 32, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+template <int MODEL>
+cudaError_t launch_solve_m(const eb::SolveParams& p, int rounds, cudaStream_t s)
+{
+  const int nb = p.nb;
+  if (nb <= 8) return launch_solve_t<MODEL, 8>(p, rounds, s);
+  if (nb <= 10) return launch_solve_t<MODEL, 10>(p, rounds, s);
+  if (nb <= 12) return launch_solve_t<MODEL, 12>(p, rounds, s);
+  if (nb <= 16) return launch_solve_t<MODEL, 16>(p, rounds, s);
+  if (nb <= 20) return launch_solve_t<MODEL, 20>(p, rounds, s);
+  if (nb <= 24) return launch_solve_t<MODEL, 24>(p, rounds, s);
+  return launch_solve_t<MODEL, 32>(p, rounds, s);
+}
+
+cudaError_t launch_solve(const eb::SolveParams& p, int model, int rounds, cudaStream_t s)
+{
+  return model == EB_MODEL_OMNI ? launch_solve_m<eb::kModelOmni>(p, rounds, s) :
+                                  launch_solve_m<eb::kModelSimpleCart>(p, rounds, s);
+}
+
+eb_status ensure_hist(eb_controller* c, long long need)
+{
+  if (need <= c->hist_cap) return EB_OK;
+  long long cap = std::max<long long>(c->hist_cap ? 2 * c->hist_cap : 128, need);
+  cap = std::min<long long>(cap, std::max<long long>((long long)c->cfg.buffer_size, need));
+  double* nh = nullptr;
+  EB_CUDA(cudaMalloc(&nh, sizeof(double) * 3 * (size_t)c->B * (size_t)cap));
+  if (c->mem_count > 0)
+    EB_CUDA(cudaMemcpyAsync(nh, c->d_hist, sizeof(double) * 3 * (size_t)c->B * (size_t)c->mem_count,
+                            cudaMemcpyDeviceToDevice, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_hist);
+  c->d_hist = nh;
+  c->hist_cap = cap;
+  return EB_OK;
+}
+
+eb_status check_fault(eb_controller* c)
+{
+  int f = 0;
+  EB_CUDA(cudaMemcpyAsync(&f, c->d_fault, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  if (f)
+  {
+    EB_CUDA(cudaMemsetAsync(c->d_fault, 0, sizeof(int), c->stream));
+    return fail(EB_ERR_INVALID_ARGUMENT, "Invalid twist y-velocity must be 0.");  // cart.hpp:169
+  }
+  return EB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+eb_status eb_create(const eb_config* cfg, eb_controller** out)
+{
+  if (!out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: out is NULL");
+  *out = nullptr;
+  if (!cfg) return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: cfg is NULL");
+  if (cfg->model != EB_MODEL_SIMPLE_CART && cfg->model != EB_MODEL_OMNI)
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: unknown model (only the 3-twist models SimpleCart and Omni "
+                                         "can be driven by ErgodicControl)");
+  if (cfg->batch < 1) return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: batch must be >= 1");
+  if (cfg->num_basis < 1 || cfg->num_basis > 32)
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: num_basis must be in 1..32");
+  if (!(cfg->dt != 0.0) || !std::isfinite(cfg->horizon / cfg->dt))
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: dt must be non-zero and finite");
+  const unsigned steps = static_cast<unsigned>(std::abs(cfg->horizon / cfg->dt));  // :199
+  if (steps == 1)                                                                   // :212-216
+    return fail(EB_ERR_INVALID_ARGUMENT,
+                "Need at least two steps in forward simulation. Increase the horizon or decrease the time step.");
+  if (steps == 0) return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: horizon / dt gives zero steps");
+  if (steps > 4096) return fail(EB_ERR_UNSUPPORTED, "eb_create: more than 4096 horizon steps is not supported");
+  if (eb_device_count() < 1) return fail(EB_ERR_NO_DEVICE, "no CUDA device is visible; there is no CPU fallback");
+  EB_CUDA(cudaSetDevice(cfg->device));
+
+  eb_controller* c = new (std::nothrow) eb_controller();
+  if (!c) return fail(EB_ERR_CUDA, "out of host memory");
+  c->cfg = *cfg;
+  c->N = (int)steps;
+  c->nb = (int)cfg->num_basis;
+  c->K = c->nb * c->nb;
+  c->B = cfg->batch;
+  const size_t utb = sizeof(double) * 3 * (size_t)c->N * c->B;
+  auto cleanup = [&](eb_status st) {
+    eb_destroy(c);
+    return st;
+  };
+#define EB_CUDA_C(expr)                                                                      \
+  do                                                                                         \
+  {                                                                                          \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return cleanup(fail(EB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__))); \
+  } while (0)
+  EB_CUDA_C(cudaMalloc(&c->d_ut[0], utb));
+  EB_CUDA_C(cudaMalloc(&c->d_ut[1], utb));
+  EB_CUDA_C(cudaMemset(c->d_ut[0], 0, utb));  // ut_ = zeros (:201)
+  EB_CUDA_C(cudaMemset(c->d_ut[1], 0, utb));
+  EB_CUDA_C(cudaMalloc(&c->d_pose, sizeof(double) * 3 * c->B));
+  EB_CUDA_C(cudaMemset(c->d_pose, 0, sizeof(double) * 3 * c->B));
+  EB_CUDA_C(cudaMalloc(&c->d_x, sizeof(double) * 3 * c->B));
+  EB_CUDA_C(cudaMalloc(&c->d_u0, sizeof(double) * 3 * c->B));
+  EB_CUDA_C(cudaMalloc(&c->d_metric, sizeof(double) * c->B));
+  EB_CUDA_C(cudaMalloc(&c->d_ck, sizeof(double) * (size_t)c->K * c->B));
+  EB_CUDA_C(cudaMemset(c->d_ck, 0, sizeof(double) * (size_t)c->K * c->B));
+  EB_CUDA_C(cudaMalloc(&c->d_phik, sizeof(double) * c->K));
+  EB_CUDA_C(cudaMemset(c->d_phik, 0, sizeof(double) * c->K));
+  EB_CUDA_C(cudaMalloc(&c->d_lamk, sizeof(double) * c->K));
+  EB_CUDA_C(cudaMalloc(&c->d_mem_idx_in, sizeof(int) * (size_t)std::max(1u, cfg->batch_size) * c->B));
+  EB_CUDA_C(cudaMalloc(&c->d_mem_idx_out, sizeof(int) * (size_t)std::max(1u, cfg->batch_size) * c->B));
+  EB_CUDA_C(cudaMalloc(&c->d_fault, sizeof(int)));
+  EB_CUDA_C(cudaMemset(c->d_fault, 0, sizeof(int)));
+  // Basis::Basis (basis.cpp:48-77): index = ky*nb + kx, lamda_k = 1/(1+sqrt(kx^2+ky^2))^1.5
+  std::vector<double> lam(c->K);
+  for (int ky = 0; ky < c->nb; ky++)
+    for (int kx = 0; kx < c->nb; kx++)
+      lam[ky * c->nb + kx] = 1.0 / std::pow(1.0 + std::sqrt((double)((long long)kx * kx + (long long)ky * ky)), 1.5);
+  EB_CUDA_C(cudaMemcpy(c->d_lamk, lam.data(), sizeof(double) * c->K, cudaMemcpyHostToDevice));
+#undef EB_CUDA_C
+  *out = c;
+  return EB_OK;
+}
+
+void eb_destroy(eb_controller* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaFree(c->d_ut[0]);
+  cudaFree(c->d_ut[1]);
+  cudaFree(c->d_pose);
+  cudaFree(c->d_hist);
+  cudaFree(c->d_phik);
+  cudaFree(c->d_lamk);
+  cudaFree(c->d_u0);
+  cudaFree(c->d_metric);
+  cudaFree(c->d_ck);
+  cudaFree(c->d_x);
+  cudaFree(c->d_mem_idx_in);
+  cudaFree(c->d_mem_idx_out);
+  cudaFree(c->d_fault);
+  cudaFree(c->d_phi_grid);
+  cudaFree(c->d_gauss);
+  eb_phik_plan_destroy(c->plan);
+  delete c;
+}
+
+eb_status eb_clone(const eb_controller* src, eb_controller** out)
+{
+  if (!src || !out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_clone: NULL argument");
+  eb_controller* c = nullptr;
+  eb_status st = eb_create(&src->cfg, &c);
+  if (st != EB_OK) return st;
+  auto bail = [&](cudaError_t e) {
+    eb_destroy(c);
+    return fail(EB_ERR_CUDA, std::string("eb_clone: ") + cudaGetErrorString(e));
+  };
+  cudaError_t e = cudaStreamSynchronize(src->stream);
+  if (e != cudaSuccess) return bail(e);
+  const size_t utb = sizeof(double) * 3 * (size_t)src->N * src->B;
+  c->cur = 0;
+  if ((e = cudaMemcpy(c->d_ut[0], src->d_ut[src->cur], utb, cudaMemcpyDeviceToDevice)) != cudaSuccess) return bail(e);
+  if ((e = cudaMemcpy(c->d_pose, src->d_pose, sizeof(double) * 3 * src->B, cudaMemcpyDeviceToDevice)) != cudaSuccess)
+    return bail(e);
+  if ((e = cudaMemcpy(c->d_phik, src->d_phik, sizeof(double) * src->K, cudaMemcpyDeviceToDevice)) != cudaSuccess)
+    return bail(e);
+  if ((e = cudaMemcpy(c->d_ck, src->d_ck, sizeof(double) * (size_t)src->K * src->B, cudaMemcpyDeviceToDevice)) !=
+      cudaSuccess)
+    return bail(e);
+  if (src->mem_count > 0)
+  {
+    st = ensure_hist(c, src->mem_count);
+    if (st != EB_OK)
+    {
+      eb_destroy(c);
+      return st;
+    }
+    if ((e = cudaMemcpy(c->d_hist, src->d_hist, sizeof(double) * 3 * (size_t)src->B * (size_t)src->mem_count,
+                        cudaMemcpyDeviceToDevice)) != cudaSuccess)
+      return bail(e);
+    c->mem_count = src->mem_count;
+  }
+  c->lx = src->lx;
+  c->ly = src->ly;
+  c->map_pos[0] = src->map_pos[0];
+  c->map_pos[1] = src->map_pos[1];
+  c->gauss_mu = src->gauss_mu;
+  c->gauss_sigma = src->gauss_sigma;
+  c->call = src->call;
+  c->have_pose = src->have_pose;
+  c->stream = src->stream;
+  *out = c;
+  return EB_OK;
+}
+
+eb_status eb_set_stream(eb_controller* c, void* s)
+{
+  if (!c) return fail(EB_ERR_INVALID_ARGUMENT, "controller is NULL");
+  c->stream = static_cast<cudaStream_t>(s);
+  if (c->plan) c->plan->stream = c->stream;
+  return EB_OK;
+}
+
+int eb_steps(const eb_controller* c) { return c ? c->N : 0; }
+int eb_num_coeff(const eb_controller* c) { return c ? c->K : 0; }
+int eb_batch(const eb_controller* c) { return c ? c->B : 0; }
+double eb_time_step(const eb_controller* c) { return c ? c->cfg.dt : 0.0; }
+long long eb_memory_size(const eb_controller* c) { return c ? c->mem_count : 0; }
+long long eb_launch_count(const eb_controller* c) { return c ? c->launches + (c->plan ? c->plan->launches : 0) : 0; }
+double* eb_ut_dev(eb_controller* c) { return c ? c->d_ut[c->cur] : nullptr; }
+double* eb_ck_dev(eb_controller* c) { return c ? c->d_ck : nullptr; }
+
+eb_status eb_set_target_gaussians(eb_controller* c, int n, const double* mu, const double* sigma)
+{
+  if (!c || n < 0 || (n > 0 && (!mu || !sigma))) return fail(EB_ERR_INVALID_ARGUMENT, "eb_set_target_gaussians: bad argument");
+  c->gauss_mu.assign(mu, mu + 2 * (size_t)n);
+  c->gauss_sigma.assign(sigma, sigma + 2 * (size_t)n);
+  return EB_OK;
+}
+
+eb_status eb_config_target(eb_controller* c, double xmin, double xmax, double ymin, double ymax, int* rebuilt)
+{
+  if (!c) return fail(EB_ERR_INVALID_ARGUMENT, "controller is NULL");
+  if (rebuilt) *rebuilt = 0;
+  // translation from map to fourier domain (:366-367)
+  c->map_pos[0] = xmin;
+  c->map_pos[1] = ymin;
+  const double mx = xmax - xmin, my = ymax - ymin;
+  if (almost_equal(mx, c->lx) && almost_equal(my, c->ly)) return EB_OK;  // :374-377
+  if (!(mx > 0.0) || !(my > 0.0)) return fail(EB_ERR_INVALID_ARGUMENT, "eb_config_target: empty map extent");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  const int nx = (int)axis_length(0.0, mx, c->cfg.resolution) + 1;  // :387-388
+  const int ny = (int)axis_length(0.0, my, c->cfg.resolution) + 1;
+  const int ng = (int)(c->gauss_mu.size() / 2);
+  if (ng == 0) return fail(EB_ERR_INVALID_ARGUMENT, "eb_config_target: no target set (call eb_set_target_gaussians)");
+  eb_phik_plan* plan = nullptr;
+  eb_status st = eb_phik_plan_create(c->cfg.device, nx, ny, c->cfg.resolution, mx, my, c->nb, &plan);
+  if (st != EB_OK) return st;
+  eb_phik_plan_destroy(c->plan);
+  c->plan = plan;
+  c->plan->stream = c->stream;
+  const size_t cells = (size_t)nx * ny;
+  if (cells > c->phi_grid_cells)
+  {
+    cudaFree(c->d_phi_grid);
+    c->d_phi_grid = nullptr;
+    c->phi_grid_cells = 0;
+    EB_CUDA(cudaMalloc(&c->d_phi_grid, sizeof(double) * cells));
+    c->phi_grid_cells = cells;
+  }
+  if (ng > c->gauss_cap)
+  {
+    cudaFree(c->d_gauss);
+    c->d_gauss = nullptr;
+    c->gauss_cap = 0;
+    EB_CUDA(cudaMalloc(&c->d_gauss, sizeof(double) * 6 * (size_t)ng));
+    c->gauss_cap = ng;
+  }
+  // Gaussian ctor (target.hpp:68-71): cov = diag(sigma^2), cov_inv = inv(cov)
+  // (2x2 cofactor inverse); operator() (:91-102) translates the mean.
+  std::vector<double> g(6 * (size_t)ng);
+  for (int i = 0; i < ng; i++)
+  {
+    const double a = c->gauss_sigma[2 * i] * c->gauss_sigma[2 * i];
+    const double d = c->gauss_sigma[2 * i + 1] * c->gauss_sigma[2 * i + 1];
+    const double det = a * d - 0.0 * 0.0;
+    g[6 * i + 0] = c->gauss_mu[2 * i] - xmin;
+    g[6 * i + 1] = c->gauss_mu[2 * i + 1] - ymin;
+    g[6 * i + 2] = d / det;     // ci(0,0)
+    g[6 * i + 3] = -0.0 / det;  // ci(1,0)
+    g[6 * i + 4] = -0.0 / det;  // ci(0,1)
+    g[6 * i + 5] = a / det;     // ci(1,1)
+  }
+  EB_CUDA(cudaMemcpyAsync(c->d_gauss, g.data(), sizeof(double) * g.size(), cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));  // g is a stack-lifetime buffer
+  eb::target_fill_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, c->stream>>>(ng, c->d_gauss, c->plan->d_xs,
+                                                                                 c->plan->d_ys, nx, ny, c->d_phi_grid);
+  c->launches += 1;
+  EB_CUDA(cudaGetLastError());
+  st = eb_phik_execute_dev(c->plan, c->d_phi_grid, c->d_phik, nullptr);
+  if (st != EB_OK) return st;
+  c->lx = mx;  // :382-383
+  c->ly = my;
+  if (rebuilt) *rebuilt = 1;
+  return EB_OK;
+}
+
+eb_status eb_set_phik(eb_controller* c, const double* phik, double lx, double ly)
+{
+  if (!c || !phik) return fail(EB_ERR_INVALID_ARGUMENT, "eb_set_phik: NULL argument");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  EB_CUDA(cudaMemcpyAsync(c->d_phik, phik, sizeof(double) * c->K, cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  c->lx = lx;
+  c->ly = ly;
+  return EB_OK;
+}
+
+eb_status eb_get_phik(const eb_controller* c, double* phik, double* lx, double* ly)
+{
+  if (!c) return fail(EB_ERR_INVALID_ARGUMENT, "controller is NULL");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  if (phik)
+  {
+    EB_CUDA(cudaMemcpyAsync(phik, c->d_phik, sizeof(double) * c->K, cudaMemcpyDeviceToHost, c->stream));
+    EB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (lx) *lx = c->lx;
+  if (ly) *ly = c->ly;
+  return EB_OK;
+}
+
+static eb_status add_state_memory(eb_controller* c, const double* x, cudaMemcpyKind kind)
+{
+  if (!c || !x) return fail(EB_ERR_INVALID_ARGUMENT, "eb_add_state_memory: NULL argument");
+  if (c->mem_count >= (long long)c->cfg.buffer_size) return EB_OK;  // buffer.cpp:56-61: dropped when full
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  eb_status st = ensure_hist(c, c->mem_count + 1);
+  if (st != EB_OK) return st;
+  EB_CUDA(cudaMemcpyAsync(c->d_hist + 3 * (size_t)c->B * (size_t)c->mem_count, x, sizeof(double) * 3 * c->B, kind,
+                          c->stream));
+  if (kind == cudaMemcpyHostToDevice) EB_CUDA(cudaStreamSynchronize(c->stream));
+  c->mem_count++;
+  return EB_OK;
+}
+
+eb_status eb_add_state_memory_host(eb_controller* c, const double* x)
+{
+  return add_state_memory(c, x, cudaMemcpyHostToDevice);
+}
+eb_status eb_add_state_memory_dev(eb_controller* c, const double* x_dev)
+{
+  return add_state_memory(c, x_dev, cudaMemcpyDeviceToDevice);
+}
+
+eb_status eb_control_dev(eb_controller* c, double xmin, double xmax, double ymin, double ymax, const double* x_dev,
+                         const int* mem_idx_dev, double* u0_dev, double* metric_dev)
+{
+  if (!c || !x_dev || !u0_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev: NULL argument");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  eb_status st = eb_config_target(c, xmin, xmax, ymin, ymax, nullptr);  // :230
+  if (st != EB_OK) return st;
+  // pose_ = x (:227)
+  if (x_dev != c->d_pose)
+    EB_CUDA(cudaMemcpyAsync(c->d_pose, x_dev, sizeof(double) * 3 * c->B, cudaMemcpyDeviceToDevice, c->stream));
+  c->have_pose = true;
+
+  eb::SolveParams p{};
+  p.B = c->B;
+  p.N = c->N;
+  p.nb = c->nb;
+  p.mem_count = (int)std::min<long long>(c->mem_count, 0x7fffffff);
+  p.batch_size = (int)c->cfg.batch_size;
+  // ReplayBuffer::sampleMemory (buffer.cpp:64-111)
+  if (c->mem_count == 0)
+    p.M = 0;
+  else if (c->mem_count <= (long long)c->cfg.batch_size)
+  {
+    p.M = (int)c->mem_count;
+    p.idx_mode = 0;
+  }
+  else
+  {
+    p.M = (int)c->cfg.batch_size;
+    p.idx_mode = mem_idx_dev ? 1 : 2;
+  }
+  c->last_idx_count = (p.M > 0 && p.idx_mode != 0) ? p.M : 0;
+  p.dt = c->cfg.dt;
+  p.lx = c->lx;
+  p.ly = c->ly;
+  p.inv_lx = 1.0 / c->lx;
+  p.inv_ly = 1.0 / c->ly;
+  p.ax = eb::kPi / c->lx;
+  p.by = eb::kPi / c->ly;
+  p.xmin = c->map_pos[0];
+  p.ymin = c->map_pos[1];
+  p.w = c->cfg.expl_weight;
+  std::memcpy(p.Rinv, c->cfg.Rinv, sizeof(p.Rinv));
+  std::memcpy(p.umin, c->cfg.umin, sizeof(p.umin));
+  std::memcpy(p.umax, c->cfg.umax, sizeof(p.umax));
+  p.bw = c->cfg.barrier_weight;
+  p.beps = c->cfg.barrier_eps;
+  p.seed = c->cfg.seed;
+  p.call = c->call++;
+  p.x = c->d_pose;
+  p.ut_in = c->d_ut[c->cur];
+  p.ut_out = c->d_ut[c->cur ^ 1];
+  p.hist = c->d_hist;
+  p.mem_idx = mem_idx_dev;
+  p.mem_idx_out = c->d_mem_idx_out;
+  p.phik = c->d_phik;
+  p.lamk = c->d_lamk;
+  p.u0 = u0_dev;
+  p.metric = metric_dev;
+  p.ck = c->d_ck;
+  p.fault = c->d_fault;
+  const int rounds = (c->N + 31) / 32;
+  cudaError_t e = launch_solve(p, c->cfg.model, rounds, c->stream);
+  if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("solve_kernel launch: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  c->cur ^= 1;
+  return EB_OK;
+}
+
+eb_status eb_check_status(eb_controller* c)
+{
+  if (!c) return fail(EB_ERR_INVALID_ARGUMENT, "controller is NULL");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  return check_fault(c);
+}
+
+eb_status eb_control_host(eb_controller* c, double xmin, double xmax, double ymin, double ymax, const double* x,
+                          const int* mem_idx, double* u0, double* metric)
+{
+  if (!c || !x || !u0) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_host: NULL argument");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  EB_CUDA(cudaMemcpyAsync(c->d_pose, x, sizeof(double) * 3 * c->B, cudaMemcpyHostToDevice, c->stream));
+  const bool need_idx = mem_idx && c->mem_count > (long long)c->cfg.batch_size;
+  if (need_idx)
+    EB_CUDA(cudaMemcpyAsync(c->d_mem_idx_in, mem_idx, sizeof(int) * (size_t)c->cfg.batch_size * c->B,
+                            cudaMemcpyHostToDevice, c->stream));
+  eb_status st = eb_control_dev(c, xmin, xmax, ymin, ymax, c->d_pose, need_idx ? c->d_mem_idx_in : nullptr, c->d_u0,
+                                metric ? c->d_metric : nullptr);
+  if (st != EB_OK) return st;
+  EB_CUDA(cudaMemcpyAsync(u0, c->d_u0, sizeof(double) * 3 * c->B, cudaMemcpyDeviceToHost, c->stream));
+  if (metric) EB_CUDA(cudaMemcpyAsync(metric, c->d_metric, sizeof(double) * c->B, cudaMemcpyDeviceToHost, c->stream));
+  return check_fault(c);  // synchronises
+}
+
+eb_status eb_opt_traj_dev(eb_controller* c, double* xt_dev)
+{
+  if (!c || !xt_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_opt_traj_dev: NULL argument");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  const int threads = 128, wpb = threads / 32;
+  const int grid = (c->B + wpb - 1) / wpb;
+  if (c->cfg.model == EB_MODEL_OMNI)
+    eb::rollout_kernel<eb::kModelOmni><<<grid, threads, 0, c->stream>>>(c->B, c->N, c->cfg.dt, c->d_pose,
+                                                                        c->d_ut[c->cur], xt_dev, c->d_fault);
+  else
+    eb::rollout_kernel<eb::kModelSimpleCart><<<grid, threads, 0, c->stream>>>(c->B, c->N, c->cfg.dt, c->d_pose,
+                                                                              c->d_ut[c->cur], xt_dev, c->d_fault);
+  c->launches += 1;
+  EB_CUDA(cudaGetLastError());
+  return EB_OK;
+}
+
+eb_status eb_opt_traj_host(eb_controller* c, double* xt)
+{
+  if (!c || !xt) return fail(EB_ERR_INVALID_ARGUMENT, "eb_opt_traj_host: NULL argument");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  const size_t bytes = sizeof(double) * 3 * (size_t)c->N * c->B;
+  double* d = nullptr;
+  EB_CUDA(cudaMalloc(&d, bytes));
+  eb_status st = eb_opt_traj_dev(c, d);
+  cudaError_t e = cudaSuccess;
+  if (st == EB_OK) e = cudaMemcpyAsync(xt, d, bytes, cudaMemcpyDeviceToHost, c->stream);
+  if (st == EB_OK && e == cudaSuccess) st = check_fault(c);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (st != EB_OK) return st;
+  if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_opt_traj_host: ") + cudaGetErrorString(e));
+  return EB_OK;
+}
+
+eb_status eb_get_ut(const eb_controller* c, double* ut)
+{
+  if (!c || !ut) return fail(EB_ERR_INVALID_ARGUMENT, "eb_get_ut: NULL argument");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  EB_CUDA(cudaMemcpyAsync(ut, c->d_ut[c->cur], sizeof(double) * 3 * (size_t)c->N * c->B, cudaMemcpyDeviceToHost,
+                          c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  return EB_OK;
+}
+
+eb_status eb_set_ut(eb_controller* c, const double* ut)
+{
+  if (!c || !ut) return fail(EB_ERR_INVALID_ARGUMENT, "eb_set_ut: NULL argument");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  EB_CUDA(cudaMemcpyAsync(c->d_ut[c->cur], ut, sizeof(double) * 3 * (size_t)c->N * c->B, cudaMemcpyHostToDevice,
+                          c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  return EB_OK;
+}
+
+eb_status eb_get_ck(const eb_controller* c, double* ck)
+{
+  if (!c || !ck) return fail(EB_ERR_INVALID_ARGUMENT, "eb_get_ck: NULL argument");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  EB_CUDA(cudaMemcpyAsync(ck, c->d_ck, sizeof(double) * (size_t)c->K * c->B, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  return EB_OK;
+}
+
+eb_status eb_get_last_mem_idx(const eb_controller* c, int* mem_idx, int* count)
+{
+  if (!c) return fail(EB_ERR_INVALID_ARGUMENT, "controller is NULL");
+  if (count) *count = c->last_idx_count;
+  if (mem_idx && c->last_idx_count > 0)
+  {
+    EB_CUDA(cudaSetDevice(c->cfg.device));
+    EB_CUDA(cudaMemcpyAsync(mem_idx, c->d_mem_idx_out, sizeof(int) * (size_t)c->cfg.batch_size * c->B,
+                            cudaMemcpyDeviceToHost, c->stream));
+    EB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return EB_OK;
+}
+
+eb_status eb_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops)
+{
+  EB_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  EB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  double* d = nullptr;
+  EB_CUDA(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t a, b;
+  EB_CUDA(cudaEventCreate(&a));
+  EB_CUDA(cudaEventCreate(&b));
+  const int grid = sms * 8, threads = 256, iters = 4096;
+  double best[2] = { 0.0, 0.0 };
+  for (int which = 0; which < 2; which++)
+    for (int rep = 0; rep < 5; rep++)
+    {
+      cudaEventRecord(a);
+      if (which == 0)
+        eb::dfma_probe<<<grid, threads>>>(d, iters, 1.0);
+      else
+        eb::dmma_probe<<<grid, threads>>>(d, iters, 1.0);
+      cudaEventRecord(b);
+      cudaError_t e = cudaEventSynchronize(b);
+      if (e != cudaSuccess)
+      {
+        cudaFree(d);
+        return fail(EB_ERR_CUDA, std::string("eb_fp64_peak: ") + cudaGetErrorString(e));
+      }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, a, b);
+      // dfma: 64 FMA per thread-iteration; dmma: 32 tiles of 8x8x4 = 256 FMA per warp-iteration
+      const double flops = which == 0 ? 2.0 * 64.0 * iters * (double)grid * threads :
+                                        2.0 * 256.0 * 32.0 * iters * (double)grid * (threads / 32);
+      if (rep > 0) best[which] = std::max(best[which], flops / (ms * 1e-3) / 1e12);
+    }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  if (dfma_tflops) *dfma_tflops = best[0];
+  if (dmma_tflops) *dmma_tflops = best[1];
+  return EB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// phik_kernels.cuh -- target density and phi_k target coefficients (sm_100a, FP64).
+//
+// Replaces Target::fill (target.cpp:78-89, Gaussian::operator() target.hpp:91-102)
+// and Basis::spatialCoeff (basis.cpp:122-133).  The reference evaluates 2K
+// cosines per grid cell into a K x G temporary; here the separable structure
+// F_k(x, y) = cos(kx a x) cos(ky b y) turns the sum over cells into
+//     phi_raw = C_y^T  Phi  C_x ,   C_x[j][kx] = cos(kx a x_j), C_y[i][ky] = cos(ky b y_i)
+// and since F_0 == 1, sum(Phi) = phi_raw[0]: normalising the density
+// (target.cpp:87) is one division after the contraction.
+//
+// This file holds the shape-agnostic kernels (any nx, ny, nb <= 32); the
+// DMMA/TMA tile kernel for large grids is in phik_dmma.cuh.
+#pragma once
+
+#include "common.cuh"
+
+namespace eb
+{
+constexpr int kPhikLd = 32;  // leading dimension of the cosine tables / T (bases padded to 32)
+
+// tab[j][k] = cos(k * (PI / l) * coord[j]) for k < nb, else 0 (basis.cpp:85)
+__global__ void cos_table_kernel(const double* __restrict__ coord, int n, double freq, int nb,
+                                 double* __restrict__ tab)
+{
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * kPhikLd) return;
+  const int j = idx / kPhikLd, k = idx % kPhikLd;
+  tab[idx] = k < nb ? cos((double)k * freq * coord[j]) : 0.0;
+}
+
+// Target::evaluate over the configTarget grid (target.cpp:68-89, un-normalised).
+// gauss: per Gaussian 6 doubles {mu_x - trans_x, mu_y - trans_y, ci00, ci10, ci01, ci11}
+__global__ void target_fill_kernel(int ng, const double* __restrict__ gauss, const double* __restrict__ xs,
+                                   const double* __restrict__ ys, int nx, int ny, double* __restrict__ phi)
+{
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= (long long)nx * ny) return;
+  const int i = (int)(c / nx), j = (int)(c % nx);
+  const double px = xs[j], py = ys[i];
+  double val = 0.0;
+  for (int g = 0; g < ng; g++)
+  {
+    const double* G = gauss + 6 * g;
+    const double d0 = px - G[0], d1 = py - G[1];
+    const double r0 = d0 * G[2] + d1 * G[3];
+    const double r1 = d0 * G[4] + d1 * G[5];
+    val += exp(-0.5 * (r0 * d0 + r1 * d1));
+  }
+  phi[c] = val;
+}
+
+// stage 1: T[i][kx] = sum_j Phi[i][j] * Cx[j][kx]; one CTA (32 x 8 threads) per row
+__global__ void __launch_bounds__(256) phik_stage1_simple(const double* __restrict__ phi, int nx,
+                                                          const double* __restrict__ cx, double* __restrict__ T)
+{
+  __shared__ double red[8][kPhikLd];
+  const int kx = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const double* row = phi + (size_t)blockIdx.x * nx;
+  double acc = 0.0;
+  for (int j = part; j < nx; j += 8) acc = fma(row[j], cx[(size_t)j * kPhikLd + kx], acc);
+  red[part][kx] = acc;
+  __syncthreads();
+  if (part == 0)
+  {
+    double s = red[0][kx];
+#pragma unroll
+    for (int pth = 1; pth < 8; pth++) s += red[pth][kx];
+    T[(size_t)blockIdx.x * kPhikLd + kx] = s;
+  }
+}
+
+// stage 2: raw[ky][kx] = sum_i Cy[i][ky] * T[i][kx]; one CTA per ky
+__global__ void __launch_bounds__(256) phik_stage2_simple(const double* __restrict__ T, int ny,
+                                                          const double* __restrict__ cyt, double* __restrict__ raw)
+{
+  __shared__ double red[8][kPhikLd];
+  const int kx = threadIdx.x & 31, part = threadIdx.x >> 5, ky = blockIdx.x;
+  double acc = 0.0;
+  for (int i = part; i < ny; i += 8) acc = fma(cyt[(size_t)i * kPhikLd + ky], T[(size_t)i * kPhikLd + kx], acc);
+  red[part][kx] = acc;
+  __syncthreads();
+  if (part == 0)
+  {
+    double s = red[0][kx];
+#pragma unroll
+    for (int pth = 1; pth < 8; pth++) s += red[pth][kx];
+    raw[ky * kPhikLd + kx] = s;
+  }
+}
+
+// sums `nparts` partial 32x32 blocks in a fixed order (deterministic) and
+// normalises: phik[ky*nb + kx] = raw[ky][kx] / raw[0][0]
+__global__ void __launch_bounds__(1024) phik_finalize(const double* __restrict__ parts, int nparts, int nb,
+                                                      double* __restrict__ phik, double* __restrict__ phi_sum)
+{
+  __shared__ double total;
+  const int t = threadIdx.x;
+  double s = 0.0;
+  for (int pth = 0; pth < nparts; pth++) s += parts[(size_t)pth * 1024 + t];
+  if (t == 0) total = s;
+  __syncthreads();
+  const int ky = t >> 5, kx = t & 31;
+  if (ky < nb && kx < nb) phik[ky * nb + kx] = s / total;
+  if (t == 0 && phi_sum) *phi_sum = total;
+}
+
+// ---- FP64 throughput probes (roofline denominator) -------------------------
+__global__ void __launch_bounds__(256) dfma_probe(double* out, int iters, double seed)
+{
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = seed + i + threadIdx.x;
+  const double m = 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; it++)
+  {
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = fma(a[i], m, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += a[i];
+  if (s == 123.456) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) dmma_probe(double* out, int iters, double seed)
+{
+  double d[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) d[i][0] = d[i][1] = seed;
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9;
+  for (int it = 0; it < iters; it++)
+  {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) dmma884(d[i][0], d[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += d[i][0] + d[i][1];
+  if (s == 123.456) out[0] = s;
+}
+}  // namespace eb

@@ -1,0 +1,491 @@
+// solve_kernel.cuh -- one receding-horizon ergodic control() iteration for a
+// batch of independent instances, fused into ONE kernel (sm_100a, FP64).
+//
+// Replaces, per instance, the body of ErgodicControl<ModelT>::control()
+// (ergodic_control.hpp:225-311): the control shift (:233-234), the RK4 forward
+// rollout (integrator.hpp:135-152,176-184), ReplayBuffer::sampleMemory
+// (buffer.cpp:64-111), Basis::trajCoeff (basis.cpp:109-120), gradErgodicMetric
+// (:419-436), gradBarrier (:454-474), the backward co-state RK4
+// (integrator.hpp:154-174,186-194 with rhodot :65-69) and updateControl
+// (:439-451), plus the ergodic metric sum_k lamda_k (c_k - phi_k)^2.
+//
+// Mapping.  One warp owns one instance; lanes are TIME STEPS.
+//  * The 3-twist models have theta' = u2, so theta_i is a prefix sum of the
+//    per-step increments and (x, y) are prefix sums of per-step RK4
+//    displacements that depend only on theta: the "sequential" RK4 chain is
+//    three warp-shuffle scans.  The co-state has the same structure backwards
+//    (A^T rho only feeds rho_2), so it is three suffix scans.
+//  * cos(k a x), sin(k a x) for k < nb come from one sincospi per state and the
+//    Chebyshev three-term recurrence (error ~ k^2 eps, << 1e-9 for nb <= 32).
+//  * c_k = (1/T) sum_t cos(ky b y_t) cos(kx a x_t) is a rank-T update of an
+//    nb x nb matrix: lanes stage their cosine rows in shared memory, and the
+//    warp contracts them with FP64 tensor-core tiles (mma.sync m8n8k4 ->
+//    DMMA.8x8x4), accumulators in registers.
+//  * the metric gradient is a pair of bilinear forms per step,
+//    sx^T (a.S) cy and cx^T (S.b) sy: each lane evaluates them for its own time
+//    step with S broadcast from shared memory, cos/sin rows held in registers.
+// Shared memory per warp: 2*NB*36 + 8*32*rounds doubles.
+#pragma once
+
+#include "common.cuh"
+
+namespace eb
+{
+constexpr int kModelSimpleCart = 0;
+constexpr int kModelOmni = 1;
+constexpr int kSolveWarps = 4;   // warps (instances in flight) per CTA
+constexpr int kTabStride = 36;   // 32 time slots + 4 pad: 36 % 16 == 4 -> conflict-free fragment loads
+constexpr int kRecFields = 8;    // per-step record: c_th, s_th, xf, yf, c_a|ex, s_a|ey, c_b, s_b
+
+struct SolveParams
+{
+  int B, N, M, nb;
+  int mem_count, batch_size, idx_mode;  // idx_mode: 0 identity, 1 from mem_idx, 2 device sampler
+  double dt, lx, ly, inv_lx, inv_ly, ax, by, xmin, ymin, w;
+  double Rinv[9], umin[3], umax[3], bw, beps;
+  unsigned long long seed, call;
+  const double* x;       // [B][3]
+  const double* ut_in;   // [B][N][3]
+  double* ut_out;        // [B][N][3]
+  const double* hist;    // [cap][B][3]
+  const int* mem_idx;    // [B][batch_size]
+  int* mem_idx_out;      // [B][batch_size]
+  const double* phik;    // [nb*nb]
+  const double* lamk;    // [nb*nb]
+  double* u0;            // [B][3]
+  double* metric;        // [B] or null
+  double* ck;            // [B][nb*nb] or null
+  int* fault;
+};
+
+template <int MODEL>
+__device__ __forceinline__ void model_f(double u0, double u1, double c, double s, double& fx, double& fy)
+{
+  if (MODEL == kModelOmni)
+  {  // omni.hpp:177-182
+    fx = u0 * c - u1 * s;
+    fy = u0 * s + u1 * c;
+  }
+  else
+  {  // cart.hpp:172
+    fx = u0 * c;
+    fy = u0 * s;
+  }
+}
+
+// Forward rollout of one round of 32 steps (integrator.hpp:135-152,176-184).
+// In: controls of this lane's step, carries (state before the round's first
+// step).  Out: post-step state of this lane's step and its heading cos/sin.
+struct RolloutCarry
+{
+  double x, y, th, cth, sth;
+};
+
+template <int MODEL>
+__device__ __forceinline__ void rollout_round(const double dt, const bool valid, const int lane, const double u0,
+                                              const double u1, const double u2, RolloutCarry& cy, double& xo,
+                                              double& yo, double& tho, double& ce, double& se)
+{
+  // theta: k1..k4 all equal u2, so the RK4 increment is (dt/6)*(u2+2u2+2u2+u2)
+  const double dth = valid ? (dt / 6.0) * (((u2 + 2.0 * u2) + 2.0 * u2) + u2) : 0.0;
+  const double inc = warp_scan_incl(dth, lane);
+  double exc = __shfl_up_sync(kFull, inc, 1);
+  if (lane == 0) exc = 0.0;
+  const double th_before = cy.th + exc;
+  tho = cy.th + inc;
+  const double thm = th_before + dt * (0.5 * u2);  // k2, k3 stage heading
+  double sm, cm;
+  sincos(tho, &se, &ce);  // k4 stage heading == post-step heading (to rounding)
+  sincos(thm, &sm, &cm);
+  double cb = __shfl_up_sync(kFull, ce, 1), sb = __shfl_up_sync(kFull, se, 1);
+  if (lane == 0)
+  {
+    cb = cy.cth;
+    sb = cy.sth;
+  }
+  double k1x, k1y, k2x, k2y, k4x, k4y;
+  model_f<MODEL>(u0, u1, cb, sb, k1x, k1y);
+  model_f<MODEL>(u0, u1, cm, sm, k2x, k2y);
+  model_f<MODEL>(u0, u1, ce, se, k4x, k4y);
+  const double dx = valid ? (dt / 6.0) * (((k1x + 2.0 * k2x) + 2.0 * k2x) + k4x) : 0.0;
+  const double dy = valid ? (dt / 6.0) * (((k1y + 2.0 * k2y) + 2.0 * k2y) + k4y) : 0.0;
+  xo = cy.x + warp_scan_incl(dx, lane);
+  yo = cy.y + warp_scan_incl(dy, lane);
+  cy.x = __shfl_sync(kFull, xo, 31);
+  cy.y = __shfl_sync(kFull, yo, 31);
+  cy.th = __shfl_sync(kFull, tho, 31);
+  cy.cth = __shfl_sync(kFull, ce, 31);
+  cy.sth = __shfl_sync(kFull, se, 31);
+}
+
+// Rank-32 update of the nb x nb coefficient accumulators from one chunk of
+// (up to) 32 states: lanes write their Chebyshev cosine rows to shared memory
+// (transposed: tab[k][t]), then the warp runs nvalid/4 DMMA k-steps.
+template <int NB>
+__device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, double* __restrict__ taby, const int lane,
+                                            const bool valid, const int nvalid, const double c1x,
+                                            const double c1y, double (&acc)[(NB + 7) / 8][(NB + 7) / 8][2])
+{
+  constexpr int TILES = (NB + 7) / 8;
+  __syncwarp();
+  {
+    // T_k(c) by the three-term recurrence, started one step early:
+    // (T_{-1}, T_0) = (c, 1) so that the first advance yields T_1 = c.
+    double xm = c1x, xk = 1.0, ym = c1y, yk = 1.0;
+    const double tx = 2.0 * c1x, ty = 2.0 * c1y;
+#pragma unroll
+    for (int k = 0; k < NB; k++)
+    {
+      tabx[k * kTabStride + lane] = valid ? xk : 0.0;
+      taby[k * kTabStride + lane] = valid ? yk : 0.0;
+      const double xn = tx * xk - xm, yn = ty * yk - ym;
+      xm = xk;
+      xk = xn;
+      ym = yk;
+      yk = yn;
+    }
+  }
+  __syncwarp();
+  const int g = lane >> 2, q = lane & 3;
+  const int ksteps = (nvalid + 3) >> 2;
+  for (int s = 0; s < ksteps; s++)
+  {
+    double a[TILES], b[TILES];
+#pragma unroll
+    for (int t = 0; t < TILES; t++)
+    {
+      const int k = 8 * t + g;
+      const bool in = (TILES * 8 == NB) || (k < NB);
+      a[t] = in ? taby[k * kTabStride + 4 * s + q] : 0.0;
+      b[t] = in ? tabx[k * kTabStride + 4 * s + q] : 0.0;
+    }
+#pragma unroll
+    for (int ti = 0; ti < TILES; ti++)
+#pragma unroll
+      for (int tj = 0; tj < TILES; tj++) dmma884(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
+  }
+}
+
+template <int MODEL, int NB>
+__global__ void __launch_bounds__(kSolveWarps * 32) solve_kernel(const SolveParams p)
+{
+  constexpr int TILES = (NB + 7) / 8;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rounds = (p.N + 31) >> 5;
+  const int npad = rounds * 32;
+  const int nb = p.nb, K = nb * nb;
+
+  // CTA-shared copies of lamda_k and phi_k (all instances share one target)
+  double* s_lam = smem;
+  double* s_phi = smem + NB * NB;
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+  {
+    s_lam[k] = p.lamk[k];
+    s_phi[k] = p.phik[k];
+  }
+  __syncthreads();
+
+  const int inst = blockIdx.x * kSolveWarps + warp;
+  if (inst >= p.B) return;
+
+  double* tabx = smem + 2 * NB * NB + warp * (2 * NB * kTabStride + kRecFields * npad);
+  double* taby = tabx + NB * kTabStride;
+  double* rec = taby + NB * kTabStride;
+  double* Ssm = tabx;  // S aliases the x table once c_k is complete
+
+  double acc[TILES][TILES][2];
+#pragma unroll
+  for (int i = 0; i < TILES; i++)
+#pragma unroll
+    for (int j = 0; j < TILES; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // ---- sampled past states (buffer.cpp:64-111), Fourier frame (:243-244) ----
+  for (int base = 0; base < p.M; base += 32)
+  {
+    const int j = base + lane;
+    const bool valid = j < p.M;
+    double c1x = 1.0, c1y = 1.0;
+    if (valid)
+    {
+      long long idx = j;  // stored <= batch_size: all states, insertion order
+      if (p.idx_mode == 1)
+        idx = p.mem_idx[(size_t)inst * p.batch_size + j];
+      else if (p.idx_mode == 2)
+      {
+        const uint64_t r = mix64(mix64(p.seed + p.call * 0xD1B54A32D192ED03ull) ^
+                                 ((uint64_t)inst * 0x9E3779B97F4A7C15ull + (uint64_t)j));
+        idx = (long long)__umul64hi(r, (uint64_t)p.mem_count);
+      }
+      if (p.idx_mode != 0 && p.mem_idx_out) p.mem_idx_out[(size_t)inst * p.batch_size + j] = (int)idx;
+      const double* h = p.hist + ((size_t)idx * p.B + inst) * 3;
+      const double xf = h[0] - p.xmin, yf = h[1] - p.ymin;
+      c1x = cospi(xf * p.inv_lx);
+      c1y = cospi(yf * p.inv_ly);
+    }
+    const int nvalid = min(32, p.M - base);
+    coeff_chunk<NB>(tabx, taby, lane, valid, nvalid, c1x, c1y, acc);
+  }
+
+  // ---- forward rollout with the shifted controls (:233-237) ----------------
+  const double* ut_in = p.ut_in + (size_t)inst * p.N * 3;
+  double* ut_out = p.ut_out + (size_t)inst * p.N * 3;
+  RolloutCarry cy;
+  {
+    const double* x0 = p.x + (size_t)inst * 3;
+    cy.x = x0[0];
+    cy.y = x0[1];
+    cy.th = x0[2];
+    sincos(cy.th, &cy.sth, &cy.cth);
+  }
+  for (int r = 0; r < rounds; r++)
+  {
+    const int i = r * 32 + lane;
+    const bool valid = i < p.N;
+    double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+    if (i + 1 < p.N)
+    {  // shift left by one column, last column zero
+      u0 = ut_in[(i + 1) * 3 + 0];
+      u1 = ut_in[(i + 1) * 3 + 1];
+      u2 = ut_in[(i + 1) * 3 + 2];
+    }
+    if (MODEL == kModelSimpleCart && !(fabs(u1 - 0.0) < 1.0e-12)) atomicOr(p.fault, 1);  // cart.hpp:167-170
+    double xo, yo, tho, ce, se;
+    rollout_round<MODEL>(p.dt, valid, lane, u0, u1, u2, cy, xo, yo, tho, ce, se);
+    const double xf = xo - p.xmin, yf = yo - p.ymin;
+    double ca, sa, cb, sb;
+    sincospi(xf * p.inv_lx, &sa, &ca);
+    sincospi(yf * p.inv_ly, &sb, &cb);
+    rec[0 * npad + i] = ce;
+    rec[1 * npad + i] = se;
+    rec[2 * npad + i] = xf;
+    rec[3 * npad + i] = yf;
+    rec[4 * npad + i] = ca;
+    rec[5 * npad + i] = sa;
+    rec[6 * npad + i] = cb;
+    rec[7 * npad + i] = sb;
+    const int nvalid = min(32, p.N - r * 32);
+    coeff_chunk<NB>(tabx, taby, lane, valid, nvalid, ca, cb, acc);
+  }
+
+  // ---- c_k, S = lamda .* (c_k - phi_k) (:422), ergodic metric ---------------
+  __syncwarp();
+  {
+    const int g = lane >> 2, q = lane & 3;
+    const double inv_t = 1.0 / (double)(p.M + p.N);  // basis.cpp:119
+    double metric = 0.0;
+#pragma unroll
+    for (int ti = 0; ti < TILES; ti++)
+#pragma unroll
+      for (int tj = 0; tj < TILES; tj++)
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+        {
+          const int ky = 8 * ti + g, kx = 8 * tj + 2 * q + e;
+          double s = 0.0;
+          if (ky < nb && kx < nb)
+          {
+            const int k = ky * nb + kx;
+            const double c = inv_t * acc[ti][tj][e];
+            const double d = c - s_phi[k];
+            s = s_lam[k] * d;
+            metric += s * d;
+            if (p.ck) p.ck[(size_t)inst * K + k] = c;
+          }
+          if (ky < NB && kx < NB) Ssm[ky * NB + kx] = s;
+        }
+    metric = warp_sum(metric);
+    if (p.metric && lane == 0) p.metric[inst] = metric;
+  }
+  __syncwarp();
+
+  // ---- gradient of the ergodic metric, one time step per lane (:419-436) ----
+  for (int r = 0; r < rounds; r++)
+  {
+    const int i = r * 32 + lane;
+    const double ca = rec[4 * npad + i], sa = rec[5 * npad + i];
+    const double cb = rec[6 * npad + i], sb = rec[7 * npad + i];
+    double cx[NB], asx[NB];  // cos(kx a x), a_kx sin(kx a x)
+    {
+      // (cos, sin)((k-1) t), (cos, sin)(k t) started at k = 0
+      double cm = ca, ck = 1.0, sm = -sa, sk = 0.0;
+      const double t2 = 2.0 * ca;
+#pragma unroll
+      for (int k = 0; k < NB; k++)
+      {
+        cx[k] = ck;
+        asx[k] = ((double)k * p.ax) * sk;
+        const double cn = t2 * ck - cm, sn = t2 * sk - sm;
+        cm = ck;
+        ck = cn;
+        sm = sk;
+        sk = sn;
+      }
+    }
+    double ex = 0.0, ey = 0.0;
+    {
+      double cm = cb, ck = 1.0, sm = -sb, sk = 0.0;  // cos/sin(ky b y), advanced in the loop
+      const double t2 = 2.0 * cb;
+#pragma unroll 2
+      for (int ky = 0; ky < NB; ky++)
+      {
+        double rx0 = 0.0, rx1 = 0.0, ry0 = 0.0, ry1 = 0.0;
+        const double* srow = Ssm + ky * NB;
+#pragma unroll
+        for (int kx = 0; kx + 1 < NB; kx += 2)
+        {
+          const double2 s2 = *reinterpret_cast<const double2*>(srow + kx);
+          rx0 = fma(s2.x, asx[kx], rx0);
+          rx1 = fma(s2.y, asx[kx + 1], rx1);
+          ry0 = fma(s2.x, cx[kx], ry0);
+          ry1 = fma(s2.y, cx[kx + 1], ry1);
+        }
+        if (NB & 1)
+        {
+          const double s1 = srow[NB - 1];
+          rx0 = fma(s1, asx[NB - 1], rx0);
+          ry0 = fma(s1, cx[NB - 1], ry0);
+        }
+        ex = fma(ck, rx0 + rx1, ex);
+        ey = fma(((double)ky * p.by) * sk, ry0 + ry1, ey);
+        const double cn = t2 * ck - cm, sn = t2 * sk - sm;
+        cm = ck;
+        ck = cn;
+        sm = sk;
+        sk = sn;
+      }
+    }
+    // dF/dx = -a sin(a x) cos(b y), dF/dy = -b cos(a x) sin(b y); times expl_weight (:433)
+    rec[4 * npad + i] = -ex * p.w;
+    rec[5 * npad + i] = -ey * p.w;
+  }
+
+  // ---- backward co-state pass + control update (:277, :439-451) -------------
+  double r0c = 0.0, r1c = 0.0, r2c = 0.0;  // rho(T) = 0 (:203)
+  for (int r = rounds - 1; r >= 0; r--)
+  {
+    const int i = r * 32 + lane;
+    const bool valid = i < p.N;
+    double u0 = 0.0, u1 = 0.0;
+    if (i + 1 < p.N)
+    {
+      u0 = ut_in[(i + 1) * 3 + 0];
+      u1 = ut_in[(i + 1) * 3 + 1];
+    }
+    const double ce = rec[0 * npad + i], se = rec[1 * npad + i];
+    const double xf = rec[2 * npad + i], yf = rec[3 * npad + i];
+    const double ex = rec[4 * npad + i], ey = rec[5 * npad + i];
+    // gradBarrier :454-474
+    double bx = 0.0, byv = 0.0;
+    bx += 2.0 * (double)(xf > p.lx - p.beps) * (xf - (p.lx - p.beps));
+    byv += 2.0 * (double)(yf > p.ly - p.beps) * (yf - (p.ly - p.beps));
+    bx += 2.0 * (double)(xf < p.beps) * (xf - p.beps);
+    byv += 2.0 * (double)(yf < p.beps) * (yf - p.beps);
+    bx *= p.bw;
+    byv *= p.bw;
+    // rhodot (:65-69): components 0 and 1 do not depend on rho
+    const double k0 = valid ? (-ex - bx) : 0.0;
+    const double k1 = valid ? (-ey - byv) : 0.0;
+    const double inc0 = -(p.dt / 6.0 * (((k0 + 2.0 * k0) + 2.0 * k0) + k0));
+    const double inc1 = -(p.dt / 6.0 * (((k1 + 2.0 * k1) + 2.0 * k1) + k1));
+    const double suf0 = warp_scan_incl_rev(inc0, lane);
+    const double suf1 = warp_scan_incl_rev(inc1, lane);
+    double exc0 = __shfl_down_sync(kFull, suf0, 1), exc1 = __shfl_down_sync(kFull, suf1, 1);
+    if (lane == 31) exc0 = exc1 = 0.0;
+    const double r0p = r0c + exc0, r1p = r1c + exc1;  // rho before this (backward) step
+    const double r0 = r0c + suf0, r1 = r1c + suf1;    // rho after it = rhot.col(i)
+    // A = fdx(x_i, u_i): only A02, A12 are non-zero
+    double a02, a12;
+    if (MODEL == kModelOmni)
+    {  // omni.hpp:195-196
+      a02 = -u0 * se - u1 * ce;
+      a12 = u0 * ce - u1 * se;
+    }
+    else
+    {  // cart.hpp:184-185
+      a02 = -u0 * se;
+      a12 = u0 * ce;
+    }
+    // component 2: k = -(A02 rho0 + A12 rho1) at the four RK4 stages
+    const double k1_2 = -(a02 * r0p + a12 * r1p);
+    const double r0s = r0p - p.dt * (0.5 * k0), r1s = r1p - p.dt * (0.5 * k1);
+    const double k2_2 = -(a02 * r0s + a12 * r1s);
+    const double r0e = r0p - p.dt * k0, r1e = r1p - p.dt * k1;
+    const double k4_2 = -(a02 * r0e + a12 * r1e);
+    const double inc2 = valid ? -(p.dt / 6.0 * (((k1_2 + 2.0 * k2_2) + 2.0 * k2_2) + k4_2)) : 0.0;
+    const double r2 = r2c + warp_scan_incl_rev(inc2, lane);
+    r0c = __shfl_sync(kFull, r0, 0);
+    r1c = __shfl_sync(kFull, r1, 0);
+    r2c = __shfl_sync(kFull, r2, 0);
+    // updateControl: u = -Rinv * (B^T rho), clamped
+    double bt0, bt1;
+    if (MODEL == kModelOmni)
+    {  // omni.hpp:208-210
+      bt0 = ce * r0 + se * r1;
+      bt1 = -se * r0 + ce * r1;
+    }
+    else
+    {  // cart.hpp:196-202
+      bt0 = ce * r0 + se * r1;
+      bt1 = 0.0;
+    }
+    if (valid)
+    {
+      double un[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+      {
+        const double v = -((p.Rinv[c + 0] * bt0 + p.Rinv[c + 3] * bt1) + p.Rinv[c + 6] * r2);
+        un[c] = clampd(v, p.umin[c], p.umax[c]);
+        ut_out[i * 3 + c] = un[c];
+      }
+      if (i == 0)
+      {
+        p.u0[(size_t)inst * 3 + 0] = un[0];
+        p.u0[(size_t)inst * 3 + 1] = un[1];
+        p.u0[(size_t)inst * 3 + 2] = un[2];
+      }
+    }
+  }
+}
+
+// optTraj() (ergodic_control.hpp:314-317): forward rollout of the CURRENT
+// control signal from the last pose, map frame, heading wrapped per step.
+template <int MODEL>
+__global__ void __launch_bounds__(128) rollout_kernel(int B, int N, double dt, const double* __restrict__ pose,
+                                                      const double* __restrict__ ut, double* __restrict__ xt,
+                                                      int* fault)
+{
+  const int lane = threadIdx.x & 31;
+  const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (inst >= B) return;
+  const double* u = ut + (size_t)inst * N * 3;
+  double* out = xt + (size_t)inst * N * 3;
+  RolloutCarry cy;
+  cy.x = pose[(size_t)inst * 3 + 0];
+  cy.y = pose[(size_t)inst * 3 + 1];
+  cy.th = pose[(size_t)inst * 3 + 2];
+  sincos(cy.th, &cy.sth, &cy.cth);
+  for (int base = 0; base < N; base += 32)
+  {
+    const int i = base + lane;
+    const bool valid = i < N;
+    double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+    if (valid)
+    {
+      u0 = u[i * 3 + 0];
+      u1 = u[i * 3 + 1];
+      u2 = u[i * 3 + 2];
+    }
+    if (MODEL == kModelSimpleCart && !(fabs(u1 - 0.0) < 1.0e-12)) atomicOr(fault, 1);
+    double xo, yo, tho, ce, se;
+    rollout_round<MODEL>(dt, valid, lane, u0, u1, u2, cy, xo, yo, tho, ce, se);
+    if (valid)
+    {
+      out[i * 3 + 0] = xo;
+      out[i * 3 + 1] = yo;
+      out[i * 3 + 2] = normalize_angle_pi(tho);
+    }
+  }
+}
+}  // namespace eb

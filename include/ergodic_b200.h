@@ -1,0 +1,191 @@
+/*
+ * ergodic_b200.h -- C ABI of the B200-native ergodic-control hot path.
+ *
+ * This is the drop-in boundary for the reference's (bostoncleek/
+ * ergodic_exploration) receding-horizon controller step
+ * ErgodicControl<ModelT>::control() and the phi_k target-coefficient
+ * contraction it depends on.  The reference has no FFI of its own: its
+ * boundary is the C++ class API (ergodic_control.hpp:72-185).  The
+ * header-only adapter include/ergodic_exploration_b200/ergodic_control.hpp
+ * re-exposes that class API (Armadillo in, Armadillo out) on top of the
+ * entry points below; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - one handle = B independent controllers ("instances") on ONE CUDA device
+ *    and one CUDA stream.  B = 1 is the reference's single-robot case.
+ *  - all matrices are column-major doubles, byte-identical to
+ *    arma::mat::memptr(): a 3xN matrix is N consecutive (x, y, theta)
+ *    triples; batched buffers are B such matrices back to back
+ *    (instance-major).
+ *  - `_host` entry points take host pointers, copy in/out and synchronise;
+ *    `_dev` entry points take device pointers, enqueue on the handle's
+ *    stream and return immediately.
+ *  - every call returns an eb_status; no exception crosses the ABI.
+ *    eb_last_error() returns the message of the last failure.  The adapter
+ *    rethrows the reference's exception types (std::invalid_argument, ...).
+ *  - there is NO CPU fallback: without a CUDA device every call fails with
+ *    EB_ERR_NO_DEVICE / EB_ERR_CUDA.
+ *
+ * Citations are file:line in the reference tree.
+ */
+#ifndef ERGODIC_B200_H
+#define ERGODIC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EB_ABI_VERSION 1
+
+typedef enum eb_status {
+  EB_OK = 0,
+  EB_ERR_INVALID_ARGUMENT = 1, /* reference: std::invalid_argument */
+  EB_ERR_OUT_OF_RANGE = 2,     /* reference: std::out_of_range (buffer.cpp:84,103) */
+  EB_ERR_CUDA = 3,             /* CUDA runtime failure (message has the cudaError) */
+  EB_ERR_NO_DEVICE = 4,        /* no usable CUDA device: there is no CPU path */
+  EB_ERR_UNSUPPORTED = 5
+} eb_status;
+
+/* models the controller can run (3-twist models only) */
+typedef enum eb_model {
+  EB_MODEL_SIMPLE_CART = 0, /* models/cart.hpp:152-206 */
+  EB_MODEL_OMNI = 1         /* models/omni.hpp:164-215 */
+} eb_model;
+
+/* Constructor arguments of ErgodicControl (ergodic_control.hpp:90-94) plus
+ * the two constants the reference hard-codes in gradBarrier (:457-458). */
+typedef struct eb_config {
+  int model;            /* eb_model */
+  int batch;            /* B >= 1 independent instances */
+  int device;           /* CUDA device ordinal */
+  double dt;            /* time step in integration */
+  double horizon;       /* control horizon; steps = (unsigned)|horizon/dt| (:199) */
+  double resolution;    /* target grid resolution (m) */
+  double expl_weight;   /* exploration_weight */
+  unsigned num_basis;   /* cosine bases per dimension, 1..32 */
+  unsigned buffer_size; /* max past states kept per instance (ReplayBuffer) */
+  unsigned batch_size;  /* past states sampled per control() */
+  double Rinv[9];       /* 3x3 column-major */
+  double umin[3];
+  double umax[3];
+  double barrier_weight; /* 25.0 in the reference (:457) */
+  double barrier_eps;    /* 0.05 in the reference (:458) */
+  unsigned long long seed; /* seed of the on-device replay sampler */
+} eb_config;
+
+typedef struct eb_controller eb_controller;
+
+/* fills cfg with the reference defaults (explore_omni.yaml / node mains) */
+void eb_config_defaults(eb_config *cfg, int model);
+
+int eb_abi_version(void);
+const char *eb_last_error(void);
+
+/* number of CUDA devices visible (0 when none; never fails) */
+int eb_device_count(void);
+
+/* ---- lifetime (ctor ergodic_control.hpp:188-222) ------------------------ */
+/* EB_ERR_INVALID_ARGUMENT when steps == 1 (:212-216). */
+eb_status eb_create(const eb_config *cfg, eb_controller **out);
+/* deep copy, including device state (the reference object is copied by
+ * value into Exploration, exploration.hpp:137-138) */
+eb_status eb_clone(const eb_controller *src, eb_controller **out);
+void eb_destroy(eb_controller *c);
+/* use the caller's CUDA stream (cudaStream_t) for all subsequent work */
+eb_status eb_set_stream(eb_controller *c, void *cuda_stream);
+
+int eb_steps(const eb_controller *c);      /* N */
+int eb_num_coeff(const eb_controller *c);  /* K = num_basis^2 */
+int eb_batch(const eb_controller *c);      /* B */
+double eb_time_step(const eb_controller *c); /* timeStep() :351-354 */
+long long eb_memory_size(const eb_controller *c); /* stored past states per instance */
+
+/* ---- target (setTarget :357-360, configTarget :363-416) ----------------- */
+/* mu, sigma: 2 x n column-major (host) */
+eb_status eb_set_target_gaussians(eb_controller *c, int n, const double *mu, const double *sigma);
+/* Rebuilds phi_k on the device when the map extent changed by >= 1e-12
+ * (:374); always records the map origin.  *rebuilt (may be NULL) = 1 if so. */
+eb_status eb_config_target(eb_controller *c, double xmin, double xmax, double ymin, double ymax,
+                           int *rebuilt);
+/* direct access to phi_k (K doubles, host) and the Fourier domain lengths */
+eb_status eb_set_phik(eb_controller *c, const double *phik, double lx, double ly);
+eb_status eb_get_phik(const eb_controller *c, double *phik, double *lx, double *ly);
+
+/* ---- replay memory (addStateMemory :345-348, buffer.cpp:54-62) ---------- */
+/* x: 3 x B.  Silently dropped when buffer_size states are stored. */
+eb_status eb_add_state_memory_host(eb_controller *c, const double *x);
+eb_status eb_add_state_memory_dev(eb_controller *c, const double *x_dev);
+
+/* ---- control() (:225-311), batched --------------------------------------
+ * x       3 x B current states (map frame)
+ * mem_idx batch_size x B int32 indices of the sampled past states, used only
+ *         when more than batch_size states are stored (replaces arma::randi,
+ *         buffer.cpp:98).  NULL -> indices are drawn on the device with a
+ *         counter-based generator (seed, call count, instance) and can be
+ *         read back with eb_get_last_mem_idx().
+ * u0      3 x B first twist of the updated control signal (ut_.col(0))
+ * metric  B ergodic metric sum_k lamda_k (c_k - phi_k)^2, may be NULL
+ * EB_ERR_INVALID_ARGUMENT if SimpleCart is given |u(1)| >= 1e-12
+ * (cart.hpp:167-170) -- detected on the device, reported by the _host call
+ * and by eb_check_status() for _dev calls. */
+eb_status eb_control_host(eb_controller *c, double xmin, double xmax, double ymin, double ymax,
+                          const double *x, const int *mem_idx, double *u0, double *metric);
+eb_status eb_control_dev(eb_controller *c, double xmin, double xmax, double ymin, double ymax,
+                         const double *x_dev, const int *mem_idx_dev, double *u0_dev,
+                         double *metric_dev);
+/* synchronises the stream and reports device-side faults of earlier _dev calls */
+eb_status eb_check_status(eb_controller *c);
+
+/* ---- optTraj() (:314-317) ------------------------------------------------ */
+/* xt: 3 x N x B, forward rollout of the current ut_ from the last pose */
+eb_status eb_opt_traj_host(eb_controller *c, double *xt);
+eb_status eb_opt_traj_dev(eb_controller *c, double *xt_dev);
+
+/* ---- controller state (checkpoint / teacher forcing) -------------------- */
+eb_status eb_get_ut(const eb_controller *c, double *ut); /* 3 x N x B host */
+eb_status eb_set_ut(eb_controller *c, const double *ut);
+eb_status eb_get_ck(const eb_controller *c, double *ck); /* K x B host, last control() */
+eb_status eb_get_last_mem_idx(const eb_controller *c, int *mem_idx, int *count); /* batch_size x B */
+/* device pointers to the resident state (valid for the handle's lifetime) */
+double *eb_ut_dev(eb_controller *c);
+double *eb_ck_dev(eb_controller *c);
+
+/* number of kernels this handle has launched so far */
+long long eb_launch_count(const eb_controller *c);
+
+/* ---- stateless phi_k (Target::fill normalisation target.cpp:87 +
+ *      Basis::spatialCoeff basis.cpp:122-133) --------------------------------
+ * phi: ny x nx dense density, x fastest (index i*nx + j), un-normalised, on the
+ * configTarget grid (x_j, y_i accumulated by += resolution from 0,
+ * ergodic_control.hpp:391-408).  Output phik[ky*nb + kx] = (C_y^T phi C_x) /
+ * sum(phi), K doubles; *phi_sum = sum(phi).
+ *
+ * A plan owns the cosine tables for one (nx, ny, resolution, lx, ly, nb) and
+ * the scratch buffers; execute runs the contraction only. */
+typedef struct eb_phik_plan eb_phik_plan;
+eb_status eb_phik_plan_create(int device, int nx, int ny, double resolution, double lx, double ly,
+                              int nb, eb_phik_plan **out);
+void eb_phik_plan_destroy(eb_phik_plan *p);
+eb_status eb_phik_plan_set_stream(eb_phik_plan *p, void *cuda_stream);
+/* algo: 0 = auto, 1 = simple (any shape), 2 = DMMA tiles (TMA-fed) */
+eb_status eb_phik_plan_set_algo(eb_phik_plan *p, int algo);
+eb_status eb_phik_execute_dev(eb_phik_plan *p, const double *phi_dev, double *phik_dev,
+                              double *phi_sum_dev);
+eb_status eb_phik_execute_host(eb_phik_plan *p, const double *phi, double *phik, double *phi_sum);
+/* one-shot convenience (host buffers): plan + execute + destroy */
+eb_status eb_phik_from_grid_host(int device, const double *phi, int nx, int ny, double resolution,
+                                 double lx, double ly, int nb, double *phik, double *phi_sum);
+long long eb_phik_launch_count(const eb_phik_plan *p);
+
+/* ---- measurement helper --------------------------------------------------
+ * Measured FP64 throughput of the device (TFLOP/s, 2 flop per FMA): a
+ * register-resident DFMA loop and an mma.sync m8n8k4 f64 (DMMA) loop.  Used
+ * as the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 figure). */
+eb_status eb_fp64_peak(int device, double *dfma_tflops, double *dmma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERGODIC_B200_H */

@@ -1,0 +1,256 @@
+"""-m gpu: parity of the CUDA control() path (through the C ABI) against the
+CPU oracle on the same seeded inputs.  Tolerances: see tests/helpers.py."""
+import numpy as np
+import pytest
+
+from helpers import (BOUNDS_10, BOUNDS_MAZE, MODEL_OMNI, MODEL_SIMPLE_CART, assert_abs_rel_close,
+                     assert_angle_close, assert_coeff_close, make_gpu, make_oracle, plant, random_states,
+                     warm_ut)
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_step(oracles, bounds, x, mem_idx=None):
+    """one control() on every oracle instance; returns u0, c_k, metric, ut"""
+    B = len(oracles)
+    u0 = np.empty((B, 3))
+    ck = np.empty((B, oracles[0].K))
+    metric = np.empty(B)
+    ut = np.empty((B, oracles[0].steps, 3))
+    for i, o in enumerate(oracles):
+        u0[i] = o.control(bounds, x[i], mem_idx=None if mem_idx is None else mem_idx[i])
+        last = o.last()
+        ck[i], metric[i] = last["ck"], last["metric"]
+        ut[i] = o.get_ut()
+    return u0, ck, metric, ut
+
+
+def _compare_step(gpu, oracles, bounds, x, mem_idx=None, tag=""):
+    metric = np.empty(gpu.batch)
+    u0 = gpu.control(bounds, x, mem_idx=mem_idx, metric=metric)
+    ou0, ock, ometric, out = _oracle_step(oracles, bounds, x, mem_idx)
+    assert_abs_rel_close(u0, ou0, f"{tag} u0")
+    assert_abs_rel_close(gpu.get_ut(), out, f"{tag} ut")
+    gck = gpu.get_ck()
+    for i in range(gpu.batch):
+        assert_coeff_close(gck[i], ock[i], f"{tag} c_k[{i}]")
+    assert_abs_rel_close(metric, ometric, f"{tag} metric")
+    return u0
+
+
+@pytest.mark.parametrize("model", [MODEL_SIMPLE_CART, MODEL_OMNI])
+@pytest.mark.parametrize("bounds", [BOUNDS_10, BOUNDS_MAZE])
+def test_c1_single_instance_closed_loop(model, bounds):
+    """config C1: fresh controller, then 5 successive steps, teacher-forced
+    (both sides are re-synchronised to the oracle's ut_ before every step)."""
+    mu = np.array([[2.5, 2.5], [8.5, 2.5]]) + np.array([bounds[0], bounds[2]])
+    gpu = make_gpu(model, 1, mu=mu)
+    orc = [make_oracle(model, mu=mu)]
+    x = np.array([[bounds[0] + 5.0, bounds[2] + 7.0, 0.3]])
+    for step in range(6):
+        u0 = _compare_step(gpu, orc, bounds, x, tag=f"step {step}")
+        gpu.set_ut(orc[0].get_ut()[None])  # teacher forcing (closed loop is chaotic)
+        x = plant(x, u0)
+    ph, lx, ly = gpu.get_phik()
+    assert_coeff_close(ph, orc[0].get_phik(), "phi_k")
+    assert abs(lx - (bounds[1] - bounds[0])) < 1e-12 and abs(ly - (bounds[3] - bounds[2])) < 1e-12
+
+
+@pytest.mark.parametrize("model", [MODEL_SIMPLE_CART, MODEL_OMNI])
+def test_free_running_three_steps(model):
+    """<= 3 free-running steps stay within tolerance (no teacher forcing)."""
+    gpu = make_gpu(model, 1)
+    orc = [make_oracle(model)]
+    x = np.array([[5.0, 7.0, 0.3]])
+    for step in range(3):
+        u0 = _compare_step(gpu, orc, BOUNDS_10, x, tag=f"free step {step}")
+        x = plant(x, u0)
+
+
+@pytest.mark.parametrize("model,nb,horizon", [
+    (MODEL_OMNI, 10, 5.0),       # C2 shape
+    (MODEL_SIMPLE_CART, 20, 10.0),  # C4 shape
+    (MODEL_OMNI, 16, 5.0),       # C5 shape
+    (MODEL_OMNI, 32, 3.3),
+    (MODEL_SIMPLE_CART, 7, 0.7),  # nb padded to the 8-wide instantiation, 7 steps
+    (MODEL_OMNI, 11, 6.5),        # nb padded to 12, 65 steps (3 rounds of 32)
+    (MODEL_OMNI, 24, 0.2),        # two steps: the minimum the ctor accepts
+])
+def test_batched_warm_state(model, nb, horizon):
+    """random initial states and warm control signals, batch of independent instances"""
+    rng = np.random.default_rng(0xE16C0D1C + nb)
+    B = 37
+    gpu = make_gpu(model, B, nb=nb, horizon=horizon)
+    orcs = [make_oracle(model, nb=nb, horizon=horizon) for _ in range(B)]
+    x = random_states(rng, B)
+    ut = warm_ut(rng, B, gpu.steps, model)
+    gpu.set_ut(ut)
+    for i, o in enumerate(orcs):
+        o.set_ut(ut[i])
+    for step in range(2):
+        u0 = _compare_step(gpu, orcs, BOUNDS_10, x, tag=f"nb={nb} step {step}")
+        gpu.set_ut(np.stack([o.get_ut() for o in orcs]))
+        x = plant(x, u0)
+
+
+@pytest.mark.parametrize("stored", [1, 10, 100, 101, 250])
+def test_replay_memory_branches(stored):
+    """empty / <= batch_size (all states, insertion order) / > batch_size
+    (explicit sample indices) branches of ReplayBuffer::sampleMemory"""
+    rng = np.random.default_rng(stored)
+    B, model, bs = 5, MODEL_OMNI, 100
+    gpu = make_gpu(model, B, batch_size=bs)
+    orcs = [make_oracle(model, batch_size=bs) for _ in range(B)]
+    for _ in range(stored):
+        past = random_states(rng, B)
+        gpu.addStateMemory(past)
+        for i, o in enumerate(orcs):
+            o.add_state_memory(past[i])
+    assert gpu.memory_size() == stored
+    x = random_states(rng, B)
+    ut = warm_ut(rng, B, gpu.steps, model)
+    gpu.set_ut(ut)
+    for i, o in enumerate(orcs):
+        o.set_ut(ut[i])
+    idx = rng.integers(0, stored, size=(B, bs)).astype(np.int32) if stored > bs else None
+    _compare_step(gpu, orcs, BOUNDS_10, x, mem_idx=idx, tag=f"stored={stored}")
+
+
+def test_device_sampler_is_replayable():
+    """with > batch_size stored states and no indices given, the device draws
+    them; feeding the drawn indices to the oracle reproduces the result"""
+    rng = np.random.default_rng(7)
+    B, model, bs = 4, MODEL_OMNI, 16
+    gpu = make_gpu(model, B, batch_size=bs)
+    orcs = [make_oracle(model, batch_size=bs) for _ in range(B)]
+    for _ in range(40):
+        past = random_states(rng, B)
+        gpu.addStateMemory(past)
+        for i, o in enumerate(orcs):
+            o.add_state_memory(past[i])
+    x = random_states(rng, B)
+    u0 = gpu.control(BOUNDS_10, x)
+    idx = gpu.last_mem_idx()
+    assert idx is not None and idx.shape == (B, bs) and idx.min() >= 0 and idx.max() < 40
+    assert len(np.unique(idx)) > bs // 2  # not degenerate
+    ou0, _, _, _ = _oracle_step(orcs, BOUNDS_10, x, idx)
+    assert_abs_rel_close(u0, ou0, "device-sampled u0")
+
+
+@pytest.mark.parametrize("model", [MODEL_SIMPLE_CART, MODEL_OMNI])
+def test_opt_traj(model):
+    rng = np.random.default_rng(3)
+    B = 9
+    gpu = make_gpu(model, B, horizon=7.0)
+    orcs = [make_oracle(model, horizon=7.0) for _ in range(B)]
+    x = random_states(rng, B)
+    ut = warm_ut(rng, B, gpu.steps, model)
+    gpu.set_ut(ut)
+    for i, o in enumerate(orcs):
+        o.set_ut(ut[i])
+    _compare_step(gpu, orcs, BOUNDS_10, x)
+    xt = gpu.optTraj()
+    oxt = np.stack([o.opt_traj() for o in orcs])
+    assert_abs_rel_close(xt[..., :2], oxt[..., :2], "optTraj xy")
+    assert_angle_close(xt[..., 2], oxt[..., 2], "optTraj theta")
+    assert np.all(xt[..., 2] >= -np.pi - 1e-12) and np.all(xt[..., 2] < np.pi + 1e-12)
+
+
+def test_barrier_active_near_walls():
+    """states hugging / outside the map edge exercise gradBarrier"""
+    B, model = 6, MODEL_OMNI
+    gpu = make_gpu(model, B)
+    orcs = [make_oracle(model) for _ in range(B)]
+    x = np.array([[0.01, 5.0, 0.0], [9.99, 5.0, 3.0], [5.0, 0.02, -1.5], [5.0, 9.98, 1.5],
+                  [-0.2, -0.1, 0.7], [10.3, 10.2, -2.0]])
+    rng = np.random.default_rng(11)
+    ut = warm_ut(rng, B, gpu.steps, model)
+    gpu.set_ut(ut)
+    for i, o in enumerate(orcs):
+        o.set_ut(ut[i])
+    _compare_step(gpu, orcs, BOUNDS_10, x, tag="barrier")
+
+
+def test_simple_cart_rejects_lateral_velocity():
+    """SimpleCart throws std::invalid_argument for |u(1)| >= 1e-12 (cart.hpp:167-170)"""
+    gpu = make_gpu(MODEL_SIMPLE_CART, 2)
+    ut = np.zeros((2, gpu.steps, 3))
+    ut[1, 5, 1] = 0.25
+    gpu.set_ut(ut)
+    with pytest.raises(ValueError, match="y-velocity"):
+        gpu.control(BOUNDS_10, np.array([[5.0, 5.0, 0.0], [4.0, 4.0, 1.0]]))
+
+
+def test_ctor_rejects_single_step_horizon():
+    """ergodic_control.hpp:212-216"""
+    with pytest.raises(ValueError, match="two steps"):
+        make_gpu(MODEL_OMNI, 1, horizon=0.1, dt=0.1)
+
+
+def test_map_growth_rebuilds_target():
+    """configTarget rebuilds phi_k only when the extent changes (:374-377)"""
+    gpu = make_gpu(MODEL_OMNI, 1)
+    orc = make_oracle(MODEL_OMNI)
+    x = np.array([[5.0, 7.0, 0.3]])
+    assert gpu.configTarget(BOUNDS_10) is True
+    assert gpu.configTarget(BOUNDS_10) is False
+    shifted = (1.0, 11.0, -2.0, 8.0)  # same extent, new origin: no rebuild, new map_pos
+    assert gpu.configTarget(shifted) is False
+    bigger = (0.0, 12.5, 0.0, 11.0)
+    for b in (BOUNDS_10, shifted, bigger):
+        u0 = gpu.control(b, x)
+        ou0 = orc.control(b, x[0])
+        assert_abs_rel_close(u0[0], ou0, f"bounds {b}")
+        assert_coeff_close(gpu.get_phik()[0], orc.get_phik(), f"phi_k {b}")
+        gpu.set_ut(orc.get_ut()[None])
+
+
+def test_clone_is_deep():
+    rng = np.random.default_rng(5)
+    gpu = make_gpu(MODEL_OMNI, 3)
+    x = random_states(rng, 3)
+    gpu.addStateMemory(x)
+    gpu.control(BOUNDS_10, x)
+    twin = gpu.clone()
+    a = gpu.control(BOUNDS_10, x)
+    b = twin.control(BOUNDS_10, x)
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(gpu.get_ut(), twin.get_ut())
+
+
+def test_sharding_is_bit_invariant():
+    """instances are independent: running a batch as two shards gives
+    bit-identical results (multi-GPU logic tested on one GPU)"""
+    rng = np.random.default_rng(9)
+    B, model = 24, MODEL_OMNI
+    x = random_states(rng, B)
+    ut = warm_ut(rng, B, 50, model)
+    whole = make_gpu(model, B)
+    whole.set_ut(ut)
+    u_whole = whole.control(BOUNDS_10, x)
+    parts = []
+    for lo, hi in ((0, 10), (10, 24)):
+        g = make_gpu(model, hi - lo)
+        g.set_ut(ut[lo:hi])
+        parts.append(g.control(BOUNDS_10, x[lo:hi]))
+    np.testing.assert_array_equal(u_whole, np.concatenate(parts))
+
+
+def test_device_path_matches_host_path():
+    import torch
+
+    rng = np.random.default_rng(13)
+    B, model = 64, MODEL_OMNI
+    x = random_states(rng, B)
+    ut = warm_ut(rng, B, 50, model)
+    a = make_gpu(model, B)
+    a.set_ut(ut)
+    u_host = a.control(BOUNDS_10, x)
+    b = make_gpu(model, B)
+    b.set_ut(ut)
+    xd = torch.from_numpy(x).cuda()
+    md = torch.empty(B, dtype=torch.float64, device="cuda")
+    ud = b.control(BOUNDS_10, xd, metric=md)
+    b.check()
+    np.testing.assert_array_equal(u_host, ud.cpu().numpy())
+    assert b.launch_count() >= 1

@@ -1,0 +1,86 @@
+"""-m gpu: phi_k target coefficients (Target::fill + Basis::spatialCoeff) on the
+GPU against the CPU oracle.  Coefficient tolerance: max|a-b|/max|b| <= 1e-9."""
+import numpy as np
+import pytest
+
+from helpers import assert_coeff_close
+from oracle.pyoracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def gaussian_mixture(rng, nx, ny, res, ng=8):
+    """un-normalised mixture, mu ~ U([0.1L, 0.9L]^2), sigma ~ U(0.02L, 0.10L)"""
+    lx, ly = (nx - 1) * res, (ny - 1) * res
+    xs, ys = np.arange(nx) * res, np.arange(ny) * res
+    phi = np.zeros((ny, nx))
+    for _ in range(ng):
+        mx, my = rng.uniform(0.1 * lx, 0.9 * lx), rng.uniform(0.1 * ly, 0.9 * ly)
+        sx, sy = rng.uniform(0.02 * lx, 0.10 * lx), rng.uniform(0.02 * ly, 0.10 * ly)
+        phi += np.exp(-0.5 * ((xs[None, :] - mx) / sx) ** 2 - 0.5 * ((ys[:, None] - my) / sy) ** 2)
+    return phi, lx, ly
+
+
+@pytest.mark.parametrize("nx,ny,nb,algo", [
+    (101, 101, 10, 0),   # the shipped default: 10 m map @ 0.1, 10x10 basis
+    (200, 319, 10, 1),   # maze extent
+    (64, 48, 32, 1),
+    (37, 29, 5, 1),      # ragged
+    (1, 1, 3, 1),        # single cell
+    (256, 128, 32, 0),
+    (512, 384, 16, 0),
+])
+def test_phik_matches_oracle(nx, ny, nb, algo):
+    from ergodic_exploration_b200 import PhikPlan
+
+    rng = np.random.default_rng(nx * 1000 + ny)
+    res = 0.1
+    phi, lx, ly = gaussian_mixture(rng, nx, ny, res)
+    lx, ly = max(lx, res), max(ly, res)
+    plan = PhikPlan(nx, ny, res, lx, ly, nb, algo=algo)
+    got = plan.execute(phi)
+    want, total = Oracle.phik_from_grid(phi, res, lx, ly, nb)
+    assert_coeff_close(got, want, f"phi_k {nx}x{ny} nb={nb}")
+    assert abs(plan.last_sum - total) <= 1e-9 * abs(total)
+    assert abs(got[0] - 1.0) < 1e-12  # phi_0 == 1 after normalisation
+
+
+def test_phik_arbitrary_density_not_separable():
+    """the kernel must not rely on Gaussian separability: random dense density"""
+    from ergodic_exploration_b200 import PhikPlan
+
+    rng = np.random.default_rng(99)
+    nx, ny, nb, res = 160, 96, 12, 0.25
+    phi = rng.random((ny, nx))
+    lx, ly = (nx - 1) * res, (ny - 1) * res
+    got = PhikPlan(nx, ny, res, lx, ly, nb).execute(phi)
+    want, _ = Oracle.phik_from_grid(phi, res, lx, ly, nb)
+    assert_coeff_close(got, want, "random density")
+
+
+def test_phik_linearity_large():
+    """size-independent property at a size the oracle cannot reach in seconds:
+    the un-normalised contraction is linear, phi_k(a+b) * sum(a+b) ==
+    phi_k(a) * sum(a) + phi_k(b) * sum(b)"""
+    from ergodic_exploration_b200 import PhikPlan
+
+    rng = np.random.default_rng(2024)
+    nx = ny = 2048
+    nb, res = 32, 0.1
+    a, lx, ly = gaussian_mixture(rng, nx, ny, res)
+    b = rng.random((ny, nx))
+    plan = PhikPlan(nx, ny, res, lx, ly, nb)
+    pa = plan.execute(a); sa = plan.last_sum
+    pb = plan.execute(b); sb = plan.last_sum
+    pab = plan.execute(a + b); sab = plan.last_sum
+    assert abs(sab - (sa + sb)) <= 1e-10 * sab
+    assert_coeff_close(pab * sab, pa * sa + pb * sb, "linearity")
+
+
+def test_plan_rejects_bad_arguments():
+    from ergodic_exploration_b200 import PhikPlan
+
+    with pytest.raises(ValueError):
+        PhikPlan(16, 16, 0.1, 1.5, 1.5, 33)
+    with pytest.raises(ValueError):
+        PhikPlan(0, 16, 0.1, 1.5, 1.5, 4)
