@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""bench.py -- ergodic control solves/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c5|c3]
+
+One "step" = one batched ErgodicControl::control() iteration (one fused CUDA
+kernel) over the workload's instances.  The default workload is BASELINE.json
+configs[1] ("c2": Omni, 10x10 basis, 4096 instances, 50-step horizon, shared
+two-Gaussian target, warm control signals, no replay memory).  Under torchrun
+(N > 1) every rank owns the same number of instances (weak scaling), there is
+no data-path collective, and the first twists are gathered with one NCCL
+all_gather per step inside the timed region.
+
+Printed JSON (one line, rank 0):
+  value      solves/s with inputs resident in HBM (CUDA events on the launching
+             stream, one event pair per step, L2 flushed between steps, max over ranks)
+  e2e        solves/s through the host-buffer C-ABI call (pinned host x in,
+             u0 out, H2D + kernel + D2H + sync inside the timed region)
+  roofline   the fused solve kernel against the MEASURED FP64 peak
+             (eb_fp64_peak: DFMA / DMMA probes; MEASURED_PEAKS.json has no FP64 figure)
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref, built from
+             the unmodified reference sources) on all host cores, bounded sample
+
+--impl reference times that CPU implementation alone on the same config.
+--workload c3 reports the phi_k contraction (grid cells*bases/s) instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: model, nb, horizon, batch per GPU, memory states, description
+    "c2": dict(model=1, nb=10, horizon=5.0, batch=4096, mem=0,
+               desc="configs[1]: Omni, 10x10 basis, 4096 instances, 50-step horizon"),
+    "c4": dict(model=0, nb=20, horizon=10.0, batch=131072, mem=0,
+               desc="configs[3] shard: SimpleCart, 20x20 basis, 131072 instances/GPU, 100-step horizon"),
+    "c5": dict(model=1, nb=16, horizon=5.0, batch=65536, mem=100,
+               desc="configs[4] step: Omni, 16x16 basis, 65536 instances, 50-step horizon, 100 replay states"),
+}
+BOUNDS = (0.0, 10.0, 0.0, 10.0)
+MU = [[2.5, 2.5], [8.5, 2.5]]
+SIGMA = [[1.5, 1.5], [1.5, 1.5]]
+DT = 0.1
+
+
+def model_params(model):
+    if model == 1:
+        return np.diag([1.0, 1.0, 2.0]), np.array([-1.0, -1.0, -2.0]), np.array([1.0, 1.0, 2.0])
+    return np.diag([1.0, 0.0, 2.0]), np.array([-1.0, 0.0, -2.0]), np.array([1.0, 0.0, 2.0])
+
+
+def flops_per_solve(K, N, M):
+    """algorithmic FP64 work of one control()"""
+    return 2 * K * (N + M) + 4 * K * N + 2 * K + 200 * N
+
+
+def bytes_per_solve(N, M):
+    """ut_ read + write, x, u0, metric, memory gather"""
+    return 2 * 24 * N + 24 + 24 + 8 + 24 * M
+
+
+def synth_inputs(wl, batch, seed):
+    """synthetic inputs: x0 ~ U([0.5,9.5]^2 x [-pi,pi)), warm ut_ ~ 0.5 U(umin,umax)"""
+    rng = np.random.default_rng(seed)
+    _, umin, umax = model_params(wl["model"])
+    steps = int(abs(wl["horizon"] / DT))
+    x = np.column_stack([rng.uniform(0.5, 9.5, batch), rng.uniform(0.5, 9.5, batch),
+                         rng.uniform(-np.pi, np.pi, batch)])
+    ut = rng.uniform(umin, umax, size=(batch, steps, 3)) * 0.5
+    mem = np.stack([np.column_stack([rng.uniform(0.5, 9.5, batch), rng.uniform(0.5, 9.5, batch),
+                                     rng.uniform(-np.pi, np.pi, batch)]) for _ in range(wl["mem"])]) \
+        if wl["mem"] else None
+    return x, ut, mem
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# CPU reference arm
+# --------------------------------------------------------------------------
+def cpu_reference_rate(wl, sample, steps, warmup, threads=None):
+    """Times the reference's CPU control() (oracle/_ref when the compiled
+    reference is available, else the C port) on `sample` instances of the
+    workload, spread over all host cores, one controller object per instance."""
+    import ctypes as C
+
+    from oracle import pyoracle
+    from oracle.pyoracle import Oracle, RefLib
+
+    pyoracle.build()
+    use_ref = RefLib.available()
+    lib = RefLib if use_ref else Oracle
+    threads = threads or os.cpu_count() or 1
+    x, ut, mem = synth_inputs(wl, sample, seed=0xE16C0D1C + 2)
+    R, umin, umax = model_params(wl["model"])
+    ctrls = []
+    for i in range(sample):
+        c = lib.create(wl["model"], DT, wl["horizon"], 0.1, 1.0, wl["nb"], 1000000, 100, R, umin, umax)
+        c.set_target(MU, SIGMA)
+        c.set_ut(ut[i])
+        if mem is not None:
+            for m in mem:
+                c.add_state_memory(m[i])
+        ctrls.append(c)
+    handles = (C.c_void_p * sample)(*[c._h for c in ctrls])
+    u0 = np.zeros((sample, 3))
+    clib = lib.lib()
+    chunks = [(lo, min(sample, lo + (sample + threads - 1) // threads))
+              for lo in range(0, sample, (sample + threads - 1) // threads)]
+    b = [C.c_double(v) for v in BOUNDS]
+    dp = C.POINTER(C.c_double)
+
+    def work(lo, hi):
+        hs = C.cast(C.byref(handles, lo * C.sizeof(C.c_void_p)), C.POINTER(C.c_void_p))
+        xp = x[lo:hi].ctypes.data_as(dp)
+        up = u0[lo:hi].ctypes.data_as(dp)
+        if use_ref:
+            clib.ref_control_many(hs, hi - lo, *b, C.c_double(0.1), xp, up)
+        else:
+            clib.eo_control_many(hs, hi - lo, *b, xp, up)
+
+    def one_step():
+        ts = [threading.Thread(target=work, args=ch) for ch in chunks]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+
+    for _ in range(max(1, warmup)):  # first call builds phi_k (excluded)
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    return {
+        "value": sample * steps / dt,
+        "unit": "solves/s",
+        "cores": len(chunks),
+        "kind": "reference" if use_ref else "port",
+        "sample": f"{sample} instances x {steps} control() steps of the workload, {len(chunks)} host threads, "
+                  f"one controller object per instance"
+                  + ("" if use_ref else " (C port: compiled reference oracle/_ref not present)"),
+        "ms_per_step": dt / steps * 1e3,
+    }
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    sample = min(wl["batch"], 4096)
+    r = cpu_reference_rate(wl, sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "ergodic control solves/sec (batched)", "value": r["value"],
+        "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "instances_per_step": sample,
+                   "note": "reference CPU path (single-threaded per instance), all host cores"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------
+def run_ours(args, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import ergodic_exploration_b200 as eb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = wl["batch"]
+    R, umin, umax = model_params(wl["model"])
+    N = int(abs(wl["horizon"] / DT))
+    K = wl["nb"] ** 2
+    x, ut, mem = synth_inputs(wl, B, seed=0xE16C0D1C + 2 + rank)
+    ctl = eb.ErgodicControl(wl["model"], DT, wl["horizon"], 0.1, 1.0, wl["nb"], 1000000, 100, R, umin, umax,
+                            batch=B, device=local_rank)
+    ctl.setTarget([eb.Gaussian(m, s) for m, s in zip(MU, SIGMA)])
+    ctl.set_ut(ut)
+    if mem is not None:
+        for m in mem:
+            ctl.addStateMemory(m)
+    M = min(wl["mem"], 100)
+
+    xd = torch.from_numpy(x).to(dev)
+    u0d = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    metd = torch.empty(B, dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * B, 3), dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_dev():
+        ctl.control(BOUNDS, xd, u0=u0d, metric=metd)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, u0d)
+
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    ctl.check()
+    torch.cuda.synchronize()
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctl.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()  # evict the previous step's ut_/x from L2 (outside the event pair)
+        a.record()
+        step_dev()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctl.launch_count() - launches0
+    ctl.check()
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # kernel-only duration for the roofline (single rank / no collective in the pair)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in kev:
+        flush.zero_()
+        a.record()
+        ctl.control(BOUNDS, xd, u0=u0d, metric=metd)
+        b.record()
+    torch.cuda.synchronize()
+    k_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+
+    # end to end through the host-buffer C-ABI call
+    xh = torch.from_numpy(x).pin_memory()
+    u0h = torch.empty((B, 3), dtype=torch.float64).pin_memory()
+    xh_np, u0h_np = xh.numpy(), u0h.numpy()
+    for _ in range(3):
+        ctl.control(BOUNDS, xh_np, u0=u0h_np)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctl.control(BOUNDS, xh_np, u0=u0h_np)  # H2D x, kernel, D2H u0 + status, sync
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e0
+    clk = clocks.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([t_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms, e2e_ms = t.tolist()
+        e2e_s = e2e_ms / 1e3
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total = world * B * args.steps
+    dfma, dmma = eb.fp64_peak(local_rank)
+    peak = max(dfma, dmma)
+    F = flops_per_solve(K, N, M)
+    achieved = F * B / (k_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    line = {
+        "metric": "ergodic control solves/sec (batched)",
+        "value": total / (t_ms * 1e-3),
+        "unit": "solves/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": t_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "instances_per_gpu": B, "num_basis": wl["nb"], "horizon_steps": N,
+                   "replay_states": M, "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                   "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks",
+                   "parallelism": f"instances sharded over {world} GPU(s), all_gather of u0 per step" if world > 1
+                   else "single GPU"},
+        "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
+        "e2e": {"value": world * B * args.steps / e2e_s, "unit": "solves/s",
+                "h2d_bytes_per_step": B * 3 * 8, "d2h_bytes_per_step": B * 3 * 8 + 4,
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                "path": "eb_control_host: pinned host x -> H2D -> fused kernel -> D2H u0 + fault flag -> sync"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"kernel": "solve_kernel", "bound": "fp64", "achieved": achieved, "peak": peak,
+                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                     "flops_per_solve": F, "kernel_ms": k_ms,
+                     "peak_source": f"measured live by eb_fp64_peak (DFMA {dfma:.2f}, DMMA {dmma:.2f} TFLOP/s); "
+                                    "MEASURED_PEAKS.json has no FP64 figure",
+                     "hbm": {"achieved": bytes_per_solve(N, M) * B / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "bytes_per_solve": bytes_per_solve(N, M),
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+    }
+    if world == 1:
+        sample = min(B, 4096)
+        line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(wl, sample, 3, 1).items() if k != "ms_per_step"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_phik(args, rank, world, local_rank):
+    """secondary metric: phi_k grid cells*bases/sec (configs[2]: 8192^2 grid, 32x32 basis)"""
+    import torch
+
+    import ergodic_exploration_b200 as eb
+
+    if rank != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    nx = ny = 8192
+    nb, res = 32, 0.1
+    lx = ly = (nx - 1) * res
+    g = torch.Generator(device=dev).manual_seed(0xE16C0D1C + 3)
+    xs = torch.arange(nx, device=dev, dtype=torch.float64) * res
+    phi = torch.zeros((ny, nx), dtype=torch.float64, device=dev)
+    for _ in range(8):  # un-normalised mixture of 8 Gaussians
+        mu = (0.1 + 0.8 * torch.rand(2, generator=g, device=dev, dtype=torch.float64)) * lx
+        sg = (0.02 + 0.08 * torch.rand(2, generator=g, device=dev, dtype=torch.float64)) * lx
+        phi += torch.exp(-0.5 * ((xs[None, :] - mu[0]) / sg[0]) ** 2 - 0.5 * ((xs[:, None] - mu[1]) / sg[1]) ** 2)
+    plan = eb.PhikPlan(nx, ny, res, lx, ly, nb, device=local_rank)
+    out = torch.empty(nb * nb, dtype=torch.float64, device=dev)
+    for _ in range(max(3, args.warmup)):
+        plan.execute(phi, out)
+    torch.cuda.synchronize()
+    l0 = plan.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        a.record()
+        plan.execute(phi, out)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    dfma, dmma = eb.fp64_peak(local_rank)
+    flops = 2.0 * nx * ny * nb + 2.0 * ny * nb * nb
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    line = {
+        "metric": "phi_k grid cells*bases/sec", "value": nx * ny * nb * nb / (ms * 1e-3), "unit": "cell*bases/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[2]: phi_k over 8192x8192 Gaussian-mixture grid, 32x32 basis",
+                   "l2": "input (512 MiB) larger than L2"},
+        "gpu_launches": int(plan.launch_count() - l0),
+        "roofline": {"kernel": "phik contraction", "bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12,
+                     "peak": max(dfma, dmma), "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / max(dfma, dmma),
+                     "traffic": None,
+                     "hbm": {"achieved": 8.0 * nx * ny / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "c3":
+        return run_phik(args, rank, world, local_rank)
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl, rank, world)
+    run_ours(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
