@@ -92,11 +92,14 @@ SIGNATURES = {
     "eb_launch_count": (C.c_longlong, [_vp]),
     "eb_phik_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                       C.POINTER(_vp)]),
+    "eb_phik_plan_create_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                           C.c_double, C.c_int, C.POINTER(_vp)]),
     "eb_phik_plan_destroy": (None, [_vp]),
     "eb_phik_plan_set_stream": (C.c_int, [_vp, _vp]),
     "eb_phik_plan_set_algo": (C.c_int, [_vp, C.c_int]),
     "eb_phik_execute_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "eb_phik_execute_host": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "eb_phik_execute_raw_dev": (C.c_int, [_vp, _vp, _vp]),
     "eb_phik_from_grid_host": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                          C.c_int, _vp, _vp]),
     "eb_phik_launch_count": (C.c_longlong, [_vp]),

@@ -264,10 +264,13 @@ class PhikPlan:
     configTarget grid (Target::fill normalisation + Basis::spatialCoeff)."""
 
     def __init__(self, nx: int, ny: int, resolution: float, lx: float, ly: float, nb: int, device: int = 0,
-                 algo: int = 0):
+                 algo: int = 0, row_begin: int = 0, ny_total: Optional[int] = None):
+        """ny rows starting at row_begin of an ny_total-row grid (default: the whole grid)"""
         self._lib = capi.load()
         h = C.c_void_p()
-        st = self._lib.eb_phik_plan_create(device, nx, ny, float(resolution), float(lx), float(ly), nb, C.byref(h))
+        ny_total = ny if ny_total is None else ny_total
+        st = self._lib.eb_phik_plan_create_rows(device, nx, ny_total, row_begin, ny, float(resolution), float(lx),
+                                                float(ly), nb, C.byref(h))
         if st == capi.EB_ERR_INVALID_ARGUMENT:
             raise ValueError(self._lib.eb_last_error().decode())
         check(st)
@@ -302,6 +305,17 @@ class PhikPlan:
         check(self._lib.eb_phik_execute_host(self._h, phi.ctypes.data, out.ctypes.data, C.byref(s)))
         self.last_sum = s.value
         return out
+
+    def execute_raw(self, phi, raw=None):
+        """un-normalised contraction of this plan's rows: (32, 32) torch tensor, raw[0, 0] = sum(phi)"""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._lib.eb_phik_plan_set_stream(self._h, C.c_void_p(s)))
+        assert _is_cuda_tensor(phi) and phi.dtype == torch.float64 and phi.is_contiguous()
+        assert phi.numel() == self.nx * self.ny
+        if raw is None:
+            raw = torch.empty((32, 32), dtype=torch.float64, device=phi.device)
+        check(self._lib.eb_phik_execute_raw_dev(self._h, C.c_void_p(phi.data_ptr()), C.c_void_p(raw.data_ptr())))
+        return raw
 
     def launch_count(self) -> int:
         return int(self._lib.eb_phik_launch_count(self._h))

@@ -74,7 +74,8 @@ std::vector<double> accumulated_axis(int n, double resolution)
 // ---------------------------------------------------------------------------
 struct eb_phik_plan
 {
-  int device = 0, nx = 0, ny = 0, nb = 0, algo = 0;
+  int device = 0, nx = 0, ny = 0, nb = 0, algo = 0;  // ny = rows held by this plan
+  int ny_total = 0, row_begin = 0;
   double resolution = 0, lx = 0, ly = 0;
   cudaStream_t stream = nullptr;
   double *d_xs = nullptr, *d_ys = nullptr;  // grid coordinates
@@ -134,10 +135,18 @@ void eb_config_defaults(eb_config* cfg, int model)
 eb_status eb_phik_plan_create(int device, int nx, int ny, double resolution, double lx, double ly, int nb,
                               eb_phik_plan** out)
 {
+  return eb_phik_plan_create_rows(device, nx, ny, 0, ny, resolution, lx, ly, nb, out);
+}
+
+eb_status eb_phik_plan_create_rows(int device, int nx, int ny_total, int row_begin, int ny, double resolution,
+                                   double lx, double ly, int nb, eb_phik_plan** out)
+{
   if (!out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create: out is NULL");
   *out = nullptr;
   if (nx < 1 || ny < 1 || nb < 1 || nb > 32)
     return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create: need nx, ny >= 1 and 1 <= nb <= 32");
+  if (row_begin < 0 || row_begin + ny > ny_total)
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create_rows: row range outside the grid");
   if (!(lx > 0.0) || !(ly > 0.0) || !(resolution > 0.0))
     return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create: lx, ly, resolution must be positive");
   EB_CUDA(cudaSetDevice(device));
@@ -146,6 +155,8 @@ eb_status eb_phik_plan_create(int device, int nx, int ny, double resolution, dou
   p->device = device;
   p->nx = nx;
   p->ny = ny;
+  p->ny_total = ny_total;
+  p->row_begin = row_begin;
   p->nb = nb;
   p->resolution = resolution;
   p->lx = lx;
@@ -153,7 +164,9 @@ eb_status eb_phik_plan_create(int device, int nx, int ny, double resolution, dou
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   p->max_parts = std::max(1, sms);
-  const std::vector<double> xs = accumulated_axis(nx, resolution), ys = accumulated_axis(ny, resolution);
+  const std::vector<double> xs = accumulated_axis(nx, resolution);
+  const std::vector<double> ys_all = accumulated_axis(row_begin + ny, resolution);
+  const std::vector<double> ys(ys_all.begin() + row_begin, ys_all.end());
   auto cleanup = [&](eb_status st) {
     eb_phik_plan_destroy(p);
     return st;
@@ -220,9 +233,24 @@ eb_status eb_phik_plan_set_algo(eb_phik_plan* p, int algo)
 
 long long eb_phik_launch_count(const eb_phik_plan* p) { return p ? p->launches : 0; }
 
+static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* phik_dev, double* phi_sum_dev,
+                              double* raw_dev);
+
 eb_status eb_phik_execute_dev(eb_phik_plan* p, const double* phi_dev, double* phik_dev, double* phi_sum_dev)
 {
   if (!p || !phi_dev || !phik_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_execute_dev: NULL argument");
+  return phik_execute(p, phi_dev, phik_dev, phi_sum_dev, nullptr);
+}
+
+eb_status eb_phik_execute_raw_dev(eb_phik_plan* p, const double* phi_dev, double* raw_dev)
+{
+  if (!p || !phi_dev || !raw_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_execute_raw_dev: NULL argument");
+  return phik_execute(p, phi_dev, nullptr, nullptr, raw_dev);
+}
+
+static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* phik_dev, double* phi_sum_dev,
+                              double* raw_dev)
+{
   EB_CUDA(cudaSetDevice(p->device));
   int algo = p->algo;
   if (algo == 0) algo = (eb::phik_dmma_supported(p->nx, p->ny) && (long long)p->nx * p->ny >= (1 << 18)) ? 2 : 1;
@@ -239,7 +267,7 @@ eb_status eb_phik_execute_dev(eb_phik_plan* p, const double* phi_dev, double* ph
     eb::phik_stage2_simple<<<32, 256, 0, p->stream>>>(p->d_T, p->ny, p->d_cy, p->d_parts);
     p->launches += 2;
   }
-  eb::phik_finalize<<<1, 1024, 0, p->stream>>>(p->d_parts, nparts, p->nb, phik_dev, phi_sum_dev);
+  eb::phik_finalize<<<1, 1024, 0, p->stream>>>(p->d_parts, nparts, p->nb, phik_dev, phi_sum_dev, raw_dev);
   p->launches += 1;
   EB_CUDA(cudaGetLastError());
   return EB_OK;

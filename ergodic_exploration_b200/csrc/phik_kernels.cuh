@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) phik_stage2_simple(const double* __restri
 // sums `nparts` partial 32x32 blocks in a fixed order (deterministic) and
 // normalises: phik[ky*nb + kx] = raw[ky][kx] / raw[0][0]
 __global__ void __launch_bounds__(1024) phik_finalize(const double* __restrict__ parts, int nparts, int nb,
-                                                      double* __restrict__ phik, double* __restrict__ phi_sum)
+                                                      double* __restrict__ phik, double* __restrict__ phi_sum,
+                                                      double* __restrict__ raw)
 {
   __shared__ double total;
   const int t = threadIdx.x;
@@ -100,7 +101,8 @@ __global__ void __launch_bounds__(1024) phik_finalize(const double* __restrict__
   if (t == 0) total = s;
   __syncthreads();
   const int ky = t >> 5, kx = t & 31;
-  if (ky < nb && kx < nb) phik[ky * nb + kx] = s / total;
+  if (raw) raw[t] = (ky < nb && kx < nb) ? s : 0.0;
+  if (phik && ky < nb && kx < nb) phik[ky * nb + kx] = s / total;
   if (t == 0 && phi_sum) *phi_sum = total;
 }
 

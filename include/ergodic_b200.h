@@ -167,6 +167,12 @@ long long eb_launch_count(const eb_controller *c);
 typedef struct eb_phik_plan eb_phik_plan;
 eb_status eb_phik_plan_create(int device, int nx, int ny, double resolution, double lx, double ly,
                               int nb, eb_phik_plan **out);
+/* Row-sharded variant for multi-GPU: the plan covers rows
+ * [row_begin, row_begin + row_count) of an ny_total-row grid; phi passed to
+ * execute holds only those rows.  Combine shards with eb_phik_execute_raw_dev
+ * + one all-reduce(sum) of the 1024 raw values, then divide by raw[0]. */
+eb_status eb_phik_plan_create_rows(int device, int nx, int ny_total, int row_begin, int row_count,
+                                   double resolution, double lx, double ly, int nb, eb_phik_plan **out);
 void eb_phik_plan_destroy(eb_phik_plan *p);
 eb_status eb_phik_plan_set_stream(eb_phik_plan *p, void *cuda_stream);
 /* algo: 0 = auto, 1 = simple (any shape), 2 = DMMA tiles (TMA-fed) */
@@ -174,6 +180,9 @@ eb_status eb_phik_plan_set_algo(eb_phik_plan *p, int algo);
 eb_status eb_phik_execute_dev(eb_phik_plan *p, const double *phi_dev, double *phik_dev,
                               double *phi_sum_dev);
 eb_status eb_phik_execute_host(eb_phik_plan *p, const double *phi, double *phik, double *phi_sum);
+/* un-normalised contraction: raw[ky*32 + kx] = (C_y^T phi C_x)[ky][kx], 1024
+ * doubles (entries with ky or kx >= nb are 0); raw[0] = sum(phi) */
+eb_status eb_phik_execute_raw_dev(eb_phik_plan *p, const double *phi_dev, double *raw_dev);
 /* one-shot convenience (host buffers): plan + execute + destroy */
 eb_status eb_phik_from_grid_host(int device, const double *phi, int nx, int ny, double resolution,
                                  double lx, double ly, int nb, double *phik, double *phi_sum);
