@@ -80,6 +80,7 @@ struct eb_phik_plan
   cudaStream_t stream = nullptr;
   double *d_xs = nullptr, *d_ys = nullptr;  // grid coordinates
   double *d_cx = nullptr, *d_cy = nullptr;  // cosine tables [n][32]
+  double* d_cxp = nullptr;                  // C_x re-laid for the DMMA tile kernel
   double *d_T = nullptr;                    // stage-1 result [ny][32]
   double *d_parts = nullptr;                // partial 32x32 blocks
   double *d_phik = nullptr, *d_sum = nullptr;  // staging for the _host call
@@ -192,6 +193,14 @@ eb_status eb_phik_plan_create_rows(int device, int nx, int ny_total, int row_beg
   eb::cos_table_kernel<<<(nx * eb::kPhikLd + 255) / 256, 256>>>(p->d_xs, nx, eb::kPi / lx, nb, p->d_cx);
   eb::cos_table_kernel<<<(ny * eb::kPhikLd + 255) / 256, 256>>>(p->d_ys, ny, eb::kPi / ly, nb, p->d_cy);
   p->launches += 2;
+  if (eb::phik_dmma_supported(nx, ny))
+  {
+    // room for the last column span's padding chunks (span <= nchunks)
+    const int rows_padded = 2 * ((nx + eb::kPdChunk - 1) / eb::kPdChunk) * eb::kPdChunk;
+    EB_CUDA_P(cudaMalloc(&p->d_cxp, sizeof(double) * (size_t)rows_padded * eb::kPdPitch));
+    eb::phik_permute_cx<<<(rows_padded * eb::kPdPitch + 255) / 256, 256>>>(p->d_cx, nx, rows_padded, p->d_cxp);
+    p->launches += 1;
+  }
   EB_CUDA_P(cudaGetLastError());
   EB_CUDA_P(cudaDeviceSynchronize());
 #undef EB_CUDA_P
@@ -207,6 +216,7 @@ void eb_phik_plan_destroy(eb_phik_plan* p)
   cudaFree(p->d_ys);
   cudaFree(p->d_cx);
   cudaFree(p->d_cy);
+  cudaFree(p->d_cxp);
   cudaFree(p->d_T);
   cudaFree(p->d_parts);
   cudaFree(p->d_phik);
@@ -257,7 +267,7 @@ static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* ph
   int nparts = 1;
   if (algo == 2)
   {
-    nparts = eb::phik_dmma_launch(phi_dev, p->nx, p->ny, p->d_cx, p->d_cy, p->d_parts, p->max_parts, p->stream);
+    nparts = eb::phik_dmma_launch(phi_dev, p->nx, p->ny, p->d_cxp, p->d_cy, p->d_parts, p->max_parts, p->stream);
     if (nparts < 0) return fail(EB_ERR_CUDA, std::string("phik_dmma_launch: ") + cudaGetErrorString(cudaGetLastError()));
     p->launches += 1;
   }

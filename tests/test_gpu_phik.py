@@ -29,6 +29,11 @@ def gaussian_mixture(rng, nx, ny, res, ng=8):
     (2, 1, 3, 1),        # single row
     (256, 128, 32, 0),
     (512, 384, 16, 0),
+    (256, 100, 32, 2),   # DMMA/TMA tile kernel, ragged row block
+    (132, 77, 10, 2),    # ragged column chunk (132 = 128 + 4)
+    (1024, 520, 32, 2),
+    (512, 64, 7, 2),
+    (1280, 1100, 24, 0),  # auto -> tile kernel
 ])
 def test_phik_matches_oracle(nx, ny, nb, algo):
     from ergodic_exploration_b200 import PhikPlan
