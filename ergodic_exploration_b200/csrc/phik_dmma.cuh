@@ -5,20 +5,25 @@
 // work: 8*nx*ny bytes (Phi read once) and 2*nx*ny*nb + 2*ny*nb^2 flops.
 //
 // Decomposition.  A work unit is 64 rows x (span * 128) columns of Phi.  A
-// persistent CTA (8 warps, one per SM) walks its units; inside a unit each warp
-// owns 8 rows and sweeps the columns:
+// persistent CTA (16 consumer warps + 1 producer warp, one CTA per SM) walks its
+// units; inside a unit consumer warp w owns rows 8*(w%8)..+8 and the (w/8)-th
+// 64-column half of every chunk:
 //     T[8 rows][32 kx] += Phi[8 rows][4 cols] * C_x[4 cols][32 kx]      (DMMA m8n8k4 x 4)
 //  * Phi is streamed straight from HBM into the A fragments: each lane keeps a
-//    rotating window of eight 32-byte loads in flight (64 KB per SM), a quad
-//    reads one full 128-byte line per row, every sector is used exactly once.
+//    rotating window of four 32-byte loads in flight (64 KB per SM), a quad
+//    reads 128 contiguous bytes per row, every sector is used exactly once.
 //  * the C_x chunk (128 columns x 32 bases, 36 KB with the conflict-free row
 //    pitch of 36 doubles) is staged in shared memory by the TMA bulk-copy engine
-//    (cp.async.bulk -> UBLKCP) into a two-stage ring guarded by mbarriers; the
-//    chunk rows are stored pre-permuted so the B-fragment loads are
-//    bank-conflict free.
-//  * at the end of a unit the warp folds its 8 x 32 tile into the running
-//    32 x 32 partial with C_y:  P[ky][kx] += C_y[8 rows][ky]^T * T  (32 DMMAs,
-//    0.4 % extra work), T transposed through a small shared-memory stage.
+//    (cp.async.bulk -> UBLKCP) into a three-stage ring with full/empty
+//    mbarriers, issued by a dedicated producer warp, so the consumer warps never
+//    meet at a CTA barrier inside a unit; the chunk rows are stored pre-permuted
+//    so the B-fragment loads are bank-conflict free.  The producer warp also
+//    runs cp.async.bulk.prefetch.L2 over the Phi rows six chunk iterations
+//    ahead, so the register window is refilled at L2 latency, not HBM latency.
+//  * at the end of a unit the two column halves' tiles are summed in a
+//    64 x 32 shared-memory stage and the CTA folds it into its running 32 x 32
+//    partial with C_y:  P[ky][kx] += C_y[64 rows][ky]^T * T, one 8 x 8 output
+//    tile per warp (16 DMMAs each, ~3 % extra work at span = 8).
 // Every CTA writes one 32 x 32 partial; phik_finalize sums them in a fixed
 // order (deterministic) and normalises by P[0][0] = sum(Phi).
 #pragma once
@@ -27,13 +32,16 @@
 
 namespace eb
 {
-constexpr int kPdRows = 64;         // rows per unit (8 warps x 8)
+constexpr int kPdRows = 64;         // rows per unit (8 row groups of 8)
 constexpr int kPdChunk = 128;       // columns per C_x chunk
 constexpr int kPdPitch = 36;        // doubles per chunk row: 36*8 B = 288 = 32 (mod 128) -> conflict-free
-constexpr int kPdWarps = 8;
+constexpr int kPdWarps = 16;        // consumer warps: 8 row groups x 2 column halves of every chunk
+constexpr int kPdThreads = (kPdWarps + 1) * 32;  // + 1 producer warp (TMA issue, L2 prefetch of Phi)
+constexpr int kPdStages = 3;        // C_x ring depth
+constexpr int kPdAhead = 6;         // Phi is prefetched into L2 this many chunk iterations ahead
 constexpr int kPdChunkBytes = kPdChunk * kPdPitch * 8;  // 36864
 constexpr int kPdStagePitch = 33;
-constexpr int kPdSmemBytes = 2 * kPdChunkBytes + kPdWarps * 8 * kPdStagePitch * 8 + 64;
+constexpr int kPdSmemBytes = kPdStages * kPdChunkBytes + kPdRows * kPdStagePitch * 8 + 128;
 
 inline bool phik_dmma_supported(int nx, int ny) { return nx % 4 == 0 && nx >= kPdChunk && ny >= 1; }
 
@@ -83,6 +91,20 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// TMA prefetch of a contiguous global range into L2 (no shared-memory destination)
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void consumer_barrier()
+{
+  asm volatile("bar.sync 1, %0;" ::"n"(kPdWarps * 32) : "memory");
+}
+
 // 32 contiguous bytes of Phi, streamed (read once: no L1 allocation)
 __device__ __forceinline__ void ldg_stream4(const double* p, bool pred, double (&v)[4])
 {
@@ -104,148 +126,198 @@ struct PhikDmmaParams
   int nx, ny, nchunks, span, nspans, nunits;
 };
 
-__global__ void __launch_bounds__(kPdWarps * 32, 1) phik_dmma_kernel(const PhikDmmaParams p)
+// iteration cursor: unit id + chunk index inside the unit, advanced without divisions
+struct PdCursor
+{
+  int unit, k, rb, cs;
+  __device__ __forceinline__ void init(const PhikDmmaParams& p, int first_unit)
+  {
+    unit = first_unit;
+    k = 0;
+    rb = unit / p.nspans;
+    cs = unit - rb * p.nspans;
+  }
+  __device__ __forceinline__ void advance(const PhikDmmaParams& p, int stride)
+  {
+    if (++k == p.span)
+    {
+      k = 0;
+      unit += stride;
+      rb = unit / p.nspans;
+      cs = unit - rb * p.nspans;
+    }
+  }
+  __device__ __forceinline__ int chunk(const PhikDmmaParams& p) const { return cs * p.span + k; }
+};
+
+__global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmmaParams p)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* cxs[2] = { reinterpret_cast<double*>(smem_raw), reinterpret_cast<double*>(smem_raw + kPdChunkBytes) };
-  double* stage_all = reinterpret_cast<double*>(smem_raw + 2 * kPdChunkBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * kPdChunkBytes + kPdWarps * 8 * kPdStagePitch * 8);
+  double* const cxs0 = reinterpret_cast<double*>(smem_raw);
+  double* const tstage = reinterpret_cast<double*>(smem_raw + kPdStages * kPdChunkBytes);  // [64][33]
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + kPdStages * kPdChunkBytes + kPdRows * kPdStagePitch * 8);
+  uint64_t* const empty = full + kPdStages;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, q = lane & 3;
-  double* stage = stage_all + warp * 8 * kPdStagePitch;
 
   if (threadIdx.x == 0)
   {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (int s = 0; s < kPdStages; s++)
+    {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kPdWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // iterations of this CTA: its units (grid-strided) x span chunks each
+  // this CTA's units are blockIdx.x, blockIdx.x + gridDim.x, ...; each is `span` chunk iterations
   const int my_units = (p.nunits > (int)blockIdx.x) ? (p.nunits - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int total_it = my_units * p.span;
 
-  // decode iteration -> (row of this lane, first column of the chunk, chunk id)
-  auto decode = [&](int it, int& row, int& col0, int& chunk) {
-    const int u = (int)blockIdx.x + (it / p.span) * (int)gridDim.x;
-    const int rb = u / p.nspans, cs = u % p.nspans;
-    chunk = cs * p.span + it % p.span;
-    row = rb * kPdRows + warp * 8 + g;
-    col0 = chunk * kPdChunk;
-  };
-
-  double P[4][4][2];
-#pragma unroll
-  for (int a = 0; a < 4; a++)
-#pragma unroll
-    for (int b = 0; b < 4; b++) P[a][b][0] = P[a][b][1] = 0.0;
-
-  double v[8][4];  // rotating window of Phi loads: group grp of the current / next chunk
-  if (total_it > 0)
+  if (warp == kPdWarps)
   {
-    int row, col0, chunk;
-    decode(0, row, col0, chunk);
-    if (threadIdx.x == 0)
-    {
-      mbar_expect_tx(&full[0], kPdChunkBytes);
-      tma_bulk_g2s(cxs[0], p.cxp + (size_t)chunk * kPdChunk * kPdPitch, kPdChunkBytes, &full[0]);
-    }
-    const double* src = p.phi + (size_t)row * p.nx + col0 + 4 * q;
+    // ===== producer warp =====
+    PdCursor cx_cur, pf_cur;
+    cx_cur.init(p, (int)blockIdx.x);
+    pf_cur.init(p, (int)blockIdx.x);
+    int pf_it = 0;
+    auto prefetch_phi = [&]() {  // 64 rows x 1 KB of the chunk at pf_cur, two rows per lane
+      const int col0 = pf_cur.chunk(p) * kPdChunk;
+      if (col0 < p.nx)
+      {
+        const uint32_t bytes = (uint32_t)min(kPdChunk, p.nx - col0) * 8u;
 #pragma unroll
-    for (int grp = 0; grp < 8; grp++)
-      ldg_stream4(src + 16 * grp, row < p.ny && col0 + 16 * grp + 4 * q < p.nx, v[grp]);
+        for (int r = 0; r < 2; r++)
+        {
+          const int row = pf_cur.rb * kPdRows + lane + 32 * r;
+          if (row < p.ny) tma_prefetch_l2(p.phi + (size_t)row * p.nx + col0, bytes);
+        }
+      }
+      pf_cur.advance(p, (int)gridDim.x);
+      pf_it++;
+    };
+    while (pf_it < min(kPdAhead, total_it)) prefetch_phi();
+    for (int it = 0; it < total_it; it++)
+    {
+      const int s = it % kPdStages;
+      if (it >= kPdStages) mbar_wait(&empty[s], ((it / kPdStages) - 1) & 1);
+      if (lane == 0)
+      {
+        mbar_expect_tx(&full[s], kPdChunkBytes);
+        tma_bulk_g2s(cxs0 + s * (kPdChunkBytes / 8), p.cxp + (size_t)cx_cur.chunk(p) * kPdChunk * kPdPitch,
+                     kPdChunkBytes, &full[s]);
+      }
+      cx_cur.advance(p, (int)gridDim.x);
+      if (pf_it < total_it) prefetch_phi();
+    }
+    return;
   }
 
+  // ===== consumer warps =====
+  const int g = lane >> 2, q = lane & 3;
+  const int rg = warp & 7, half = warp >> 3;
+
+  double P[2] = { 0.0, 0.0 };  // this warp's 8x8 tile of the CTA's 32x32 partial
   double T[4][2];
 #pragma unroll
   for (int t = 0; t < 4; t++) T[t][0] = T[t][1] = 0.0;
 
+  PdCursor ld_cur;  // the chunk whose Phi is being LOADED (one iteration ahead of the compute)
+  ld_cur.init(p, (int)blockIdx.x);
+  int cur_rb = ld_cur.rb;
+
+  double v[4][4];  // rotating window of Phi loads: 16-column group grp of the current / next chunk
+  if (total_it > 0)
+  {
+    const int row = ld_cur.rb * kPdRows + rg * 8 + g, col0 = ld_cur.chunk(p) * kPdChunk + half * 64;
+    const double* src = p.phi + (size_t)row * p.nx + col0 + 4 * q;
+#pragma unroll
+    for (int grp = 0; grp < 4; grp++)
+      ldg_stream4(src + 16 * grp, row < p.ny && col0 + 16 * grp + 4 * q < p.nx, v[grp]);
+    ld_cur.advance(p, (int)gridDim.x);
+  }
+
+  int k_in_unit = 0;
   for (int it = 0; it < total_it; it++)
   {
-    const int cur = it & 1;
-    int row, col0, chunk;
-    decode(it, row, col0, chunk);
-    // next iteration's C_x chunk into the other stage (freed by the barrier at
-    // the end of the previous iteration) and this lane's next Phi pointer
+    const int s = it % kPdStages;
     const bool has_next = it + 1 < total_it;
-    int nrow = 0, ncol0 = 0, nchunk = 0;
-    if (has_next) decode(it + 1, nrow, ncol0, nchunk);
-    if (has_next && threadIdx.x == 0)
-    {
-      mbar_expect_tx(&full[cur ^ 1], kPdChunkBytes);
-      tma_bulk_g2s(cxs[cur ^ 1], p.cxp + (size_t)nchunk * kPdChunk * kPdPitch, kPdChunkBytes, &full[cur ^ 1]);
-    }
+    const int nrow = ld_cur.rb * kPdRows + rg * 8 + g, ncol0 = ld_cur.chunk(p) * kPdChunk + half * 64;
+    const int next_rb = ld_cur.rb;
     const double* nsrc = p.phi + (size_t)nrow * p.nx + ncol0 + 4 * q;
     const bool nrow_ok = has_next && nrow < p.ny;
+    if (has_next) ld_cur.advance(p, (int)gridDim.x);
 
-    mbar_wait(&full[cur], (it >> 1) & 1);
-    const double* cs = cxs[cur];
+    mbar_wait(&full[s], (it / kPdStages) & 1);
+    const double* bbase = cxs0 + s * (kPdChunkBytes / 8) + (half * 64 + q) * kPdPitch + g;
 #pragma unroll
-    for (int grp = 0; grp < 8; grp++)
+    for (int grp = 0; grp < 4; grp++)
     {
 #pragma unroll
-      for (int s = 0; s < 4; s++)
+      for (int st = 0; st < 4; st++)
       {
-        const double a = v[grp][s];
-        const double* brow = cs + (16 * grp + 4 * s + q) * kPdPitch + g;
+        const double a = v[grp][st];
+        const double* brow = bbase + (16 * grp + 4 * st) * kPdPitch;
 #pragma unroll
         for (int t = 0; t < 4; t++) dmma884(T[t][0], T[t][1], a, brow[8 * t]);
       }
       // refill this slot with the same group of the next chunk
       ldg_stream4(nsrc + 16 * grp, nrow_ok && ncol0 + 16 * grp + 4 * q < p.nx, v[grp]);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the C_x stage
 
-    if ((it % p.span) == p.span - 1)
+    if (++k_in_unit == p.span)
     {
-      // unit finished: P += C_y[rows]^T * T.  T (C layout: row g, cols 8t+2q+e)
-      // goes through the warp's stage to become B fragments (row 4h+q, col 8t+g).
-      __syncwarp();
-#pragma unroll
-      for (int t = 0; t < 4; t++)
+      // Unit finished.  Sum the two column halves' tiles in the stage
+      // (C layout: row 8*rg + g, cols 8t + 2q + e), then fold with C_y.
+      k_in_unit = 0;
+      double* trow = tstage + (rg * 8 + g) * kPdStagePitch + 2 * q;
+      if (half == 0)
       {
-        stage[g * kPdStagePitch + 8 * t + 2 * q + 0] = T[t][0];
-        stage[g * kPdStagePitch + 8 * t + 2 * q + 1] = T[t][1];
-        T[t][0] = T[t][1] = 0.0;
-      }
-      __syncwarp();
-      const int rbase = row - g;  // first row of this warp's 8
 #pragma unroll
-      for (int h = 0; h < 2; h++)
+        for (int t = 0; t < 4; t++)
+        {
+          trow[8 * t + 0] = T[t][0];
+          trow[8 * t + 1] = T[t][1];
+        }
+      }
+      consumer_barrier();
+      if (half == 1)
       {
-        const int r = rbase + 4 * h + q;
-        double a[4], b[4];
 #pragma unroll
-        for (int m = 0; m < 4; m++) a[m] = r < p.ny ? __ldg(p.cy + (size_t)r * 32 + 8 * m + g) : 0.0;
-#pragma unroll
-        for (int t = 0; t < 4; t++) b[t] = stage[(4 * h + q) * kPdStagePitch + 8 * t + g];
-#pragma unroll
-        for (int m = 0; m < 4; m++)
-#pragma unroll
-          for (int t = 0; t < 4; t++) dmma884(P[m][t][0], P[m][t][1], a[m], b[t]);
+        for (int t = 0; t < 4; t++)
+        {
+          trow[8 * t + 0] += T[t][0];
+          trow[8 * t + 1] += T[t][1];
+        }
       }
+#pragma unroll
+      for (int t = 0; t < 4; t++) T[t][0] = T[t][1] = 0.0;
+      consumer_barrier();
+      // warp w owns output tile (m, t) = (w / 4, w % 4):
+      // P[8m + g][8t + 2q + e] += sum_rows C_y[row][8m + g] * T[row][8t + ..]
+      const int m = warp >> 2, t = warp & 3;
+      const int r0 = cur_rb * kPdRows;
+#pragma unroll 4
+      for (int h = 0; h < kPdRows / 4; h++)
+      {
+        const int r = r0 + 4 * h + q;
+        const double a = r < p.ny ? __ldg(p.cy + (size_t)r * 32 + 8 * m + g) : 0.0;
+        const double b = tstage[(4 * h + q) * kPdStagePitch + 8 * t + g];
+        dmma884(P[0], P[1], a, b);
+      }
+      cur_rb = next_rb;
+      consumer_barrier();  // the T stage may be overwritten by the next unit
     }
-    __syncthreads();  // everyone is done with cxs[cur]: it may be refilled next iteration
   }
 
-  // reduce the 8 warps' partials in a fixed order (reusing the C_x ring)
-  double* red = reinterpret_cast<double*>(smem_raw);  // [8][1024]
-#pragma unroll
-  for (int m = 0; m < 4; m++)
-#pragma unroll
-    for (int t = 0; t < 4; t++)
-    {
-      red[warp * 1024 + (8 * m + g) * 32 + 8 * t + 2 * q + 0] = P[m][t][0];
-      red[warp * 1024 + (8 * m + g) * 32 + 8 * t + 2 * q + 1] = P[m][t][1];
-    }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 1024; e += blockDim.x)
   {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kPdWarps; w++) s += red[w * 1024 + e];
-    p.parts[(size_t)blockIdx.x * 1024 + e] = s;
+    const int m = warp >> 2, t = warp & 3;
+    double* out = p.parts + (size_t)blockIdx.x * 1024 + (8 * m + g) * 32 + 8 * t + 2 * q;
+    out[0] = P[0];
+    out[1] = P[1];
   }
 }
 
@@ -292,7 +364,7 @@ inline int phik_dmma_launch(const double* phi, int nx, int ny, const double* cxp
       return -1;
     configured = true;
   }
-  phik_dmma_kernel<<<grid, kPdWarps * 32, kPdSmemBytes, stream>>>(p);
+  phik_dmma_kernel<<<grid, kPdThreads, kPdSmemBytes, stream>>>(p);
   if (cudaGetLastError() != cudaSuccess) return -1;
   return grid;
 }

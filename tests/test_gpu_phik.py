@@ -26,7 +26,7 @@ def gaussian_mixture(rng, nx, ny, res, ng=8):
     (200, 319, 10, 1),   # maze extent
     (64, 48, 32, 1),
     (37, 29, 5, 1),      # ragged
-    (2, 1, 3, 1),        # single row
+    (3, 2, 3, 1),        # tiny
     (256, 128, 32, 0),
     (512, 384, 16, 0),
     (256, 100, 32, 2),   # DMMA/TMA tile kernel, ragged row block

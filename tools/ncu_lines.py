@@ -36,6 +36,7 @@ def main():
             hdr = r
             si = hdr.index("Warp Stall Sampling (All Samples)")
             ie = hdr.index("Instructions Executed")
+            stall_cols = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
             continue
         if hdr is None or not active:
             continue
@@ -47,14 +48,20 @@ def main():
             except ValueError:
                 continue
             key = (cur_file, int(line_no))
-            a = agg.setdefault(key, [0, 0, line_src])
+            a = agg.setdefault(key, [0, 0, line_src, {}])
             a[0] += s
             a[1] += n
+            for i, name in stall_cols:
+                try:
+                    a[3][name] = a[3].get(name, 0) + int(r[i] or 0)
+                except (ValueError, IndexError):
+                    pass
     tot = sum(a[0] for a in agg.values()) or 1
     toti = sum(a[1] for a in agg.values()) or 1
     print(f"kernel: {first_kernel}\ntotal stall samples {tot}, warp instructions {toti}")
-    for (f, l), (s, n, src) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-        print(f"{s:7d} {100 * s / tot:5.1f}%  inst {n:9d} {100 * n / toti:5.1f}%  {f}:{l}: {src.strip()[:90]}")
+    for (f, l), (s, n, src, st) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+        why = ", ".join(f"{k}={v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:4] if v)
+        print(f"{s:7d} {100 * s / tot:5.1f}%  inst {n:9d} {100 * n / toti:5.1f}%  {f}:{l}: {src.strip()[:70]}\n{'':20s}[{why}]")
 
 
 if __name__ == "__main__":
