@@ -103,6 +103,10 @@ SIGNATURES = {
     "eb_phik_from_grid_host": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                          C.c_int, _vp, _vp]),
     "eb_phik_launch_count": (C.c_longlong, [_vp]),
+    "eb_basis_traj_coeff_host": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+    "eb_basis_grad_host": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, _vp, _vp]),
+    "eb_basis_spatial_coeff_host": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, _vp, _vp, C.c_longlong, _vp]),
+    "eb_target_fill_host": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_longlong, _vp]),
     "eb_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
 }
 

@@ -872,6 +872,103 @@ eb_status eb_get_last_mem_idx(const eb_controller* c, int* mem_idx, int* count)
   return EB_OK;
 }
 
+namespace
+{
+struct DevBuf
+{
+  double* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(double) * (n ? n : 1)); }
+};
+
+// Gaussian ctor (target.hpp:68-71) + mean translation (:100): 6 doubles per Gaussian
+std::vector<double> pack_gaussians(int ng, const double* mu, const double* sigma, const double* trans)
+{
+  std::vector<double> g(6 * (size_t)ng);
+  for (int i = 0; i < ng; i++)
+  {
+    const double a = sigma[2 * i] * sigma[2 * i], d = sigma[2 * i + 1] * sigma[2 * i + 1];
+    const double det = a * d - 0.0 * 0.0;
+    g[6 * i + 0] = mu[2 * i] - trans[0];
+    g[6 * i + 1] = mu[2 * i + 1] - trans[1];
+    g[6 * i + 2] = d / det;
+    g[6 * i + 3] = -0.0 / det;
+    g[6 * i + 4] = -0.0 / det;
+    g[6 * i + 5] = a / det;
+  }
+  return g;
+}
+}  // namespace
+
+static eb_status basis_sum(int device, double lx, double ly, int nb, const double* pts, int ld, long long n,
+                           const double* w, double scale, double* out)
+{
+  if (nb < 1 || nb > 32 || n < 1 || !pts || !out || ld < 2)
+    return fail(EB_ERR_INVALID_ARGUMENT, "Basis: need 1 <= num_basis <= 32, at least one point, ld >= 2");
+  EB_CUDA(cudaSetDevice(device));
+  DevBuf dp, dw, dout;
+  EB_CUDA(dp.alloc((size_t)ld * n));
+  EB_CUDA(dout.alloc((size_t)nb * nb));
+  EB_CUDA(cudaMemcpy(dp.p, pts, sizeof(double) * ld * n, cudaMemcpyHostToDevice));
+  if (w)
+  {
+    EB_CUDA(dw.alloc((size_t)n));
+    EB_CUDA(cudaMemcpy(dw.p, w, sizeof(double) * n, cudaMemcpyHostToDevice));
+  }
+  eb::basis_sum_kernel<<<nb * nb, 256>>>(lx, ly, nb, dp.p, ld, n, w ? dw.p : nullptr, scale, dout.p);
+  EB_CUDA(cudaGetLastError());
+  EB_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * nb * nb, cudaMemcpyDeviceToHost));
+  return EB_OK;
+}
+
+eb_status eb_basis_traj_coeff_host(int device, double lx, double ly, int nb, const double* xt, int ld, int ncols,
+                                   double* ck)
+{
+  return basis_sum(device, lx, ly, nb, xt, ld, ncols, nullptr, ncols > 0 ? 1.0 / (double)ncols : 0.0, ck);
+}
+
+eb_status eb_basis_spatial_coeff_host(int device, double lx, double ly, int nb, const double* phi_vals,
+                                      const double* phi_grid, long long G, double* phik)
+{
+  if (!phi_vals) return fail(EB_ERR_INVALID_ARGUMENT, "Basis::spatialCoeff: phi_vals is NULL");
+  return basis_sum(device, lx, ly, nb, phi_grid, 2, G, phi_vals, 1.0, phik);
+}
+
+eb_status eb_basis_grad_host(int device, double lx, double ly, int nb, const double* x, double* dfk)
+{
+  if (nb < 1 || nb > 32 || !x || !dfk) return fail(EB_ERR_INVALID_ARGUMENT, "Basis::gradFourierBasis: bad argument");
+  EB_CUDA(cudaSetDevice(device));
+  DevBuf d;
+  EB_CUDA(d.alloc(2 * (size_t)nb * nb));
+  eb::basis_grad_kernel<<<(nb * nb + 127) / 128, 128>>>(lx, ly, nb, x[0], x[1], d.p);
+  EB_CUDA(cudaGetLastError());
+  EB_CUDA(cudaMemcpy(dfk, d.p, sizeof(double) * 2 * nb * nb, cudaMemcpyDeviceToHost));
+  return EB_OK;
+}
+
+eb_status eb_target_fill_host(int device, int ng, const double* mu, const double* sigma, const double* trans,
+                              const double* phi_grid, long long G, double* phi_vals)
+{
+  if (ng < 1 || !mu || !sigma || !trans || !phi_grid || !phi_vals || G < 1)
+    return fail(EB_ERR_INVALID_ARGUMENT, "Target::fill: bad argument");
+  EB_CUDA(cudaSetDevice(device));
+  const std::vector<double> g = pack_gaussians(ng, mu, sigma, trans);
+  DevBuf dg, dp, dv, dt;
+  EB_CUDA(dg.alloc(g.size()));
+  EB_CUDA(dp.alloc(2 * (size_t)G));
+  EB_CUDA(dv.alloc((size_t)G));
+  EB_CUDA(dt.alloc(1));
+  EB_CUDA(cudaMemcpy(dg.p, g.data(), sizeof(double) * g.size(), cudaMemcpyHostToDevice));
+  EB_CUDA(cudaMemcpy(dp.p, phi_grid, sizeof(double) * 2 * G, cudaMemcpyHostToDevice));
+  const unsigned blocks = (unsigned)((G + 255) / 256);
+  eb::target_points_kernel<<<blocks, 256>>>(ng, dg.p, dp.p, G, dv.p);
+  eb::vector_sum_kernel<<<1, 1024>>>(dv.p, G, dt.p);
+  eb::vector_div_kernel<<<blocks, 256>>>(dv.p, G, dt.p);  // target.cpp:87
+  EB_CUDA(cudaGetLastError());
+  EB_CUDA(cudaMemcpy(phi_vals, dv.p, sizeof(double) * G, cudaMemcpyDeviceToHost));
+  return EB_OK;
+}
+
 eb_status eb_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops)
 {
   EB_CUDA(cudaSetDevice(device));

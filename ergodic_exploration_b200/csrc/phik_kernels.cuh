@@ -106,6 +106,85 @@ __global__ void __launch_bounds__(1024) phik_finalize(const double* __restrict__
   if (t == 0 && phi_sum) *phi_sum = total;
 }
 
+// ---- point-wise Basis / Target entry points (arbitrary points, not a grid) ---
+// One CTA per coefficient k = ky*nb + kx; threads stride over the points.
+// mode 0: out[k] = scale * sum_c F_k(p_c) * w_c   (Basis::trajCoeff basis.cpp:109-120 with w = 1,
+//                                                 Basis::spatialCoeff :122-133 with w = phi_vals)
+__global__ void __launch_bounds__(256) basis_sum_kernel(double lx, double ly, int nb, const double* __restrict__ pts,
+                                                        int ld, long long n, const double* __restrict__ w,
+                                                        double scale, double* __restrict__ out)
+{
+  __shared__ double red[256];
+  const int k = blockIdx.x, kx = k % nb, ky = k / nb;
+  const double fx = (double)kx * (kPi / lx), fy = (double)ky * (kPi / ly);  // basis.cpp:85
+  double acc = 0.0;
+  for (long long c = threadIdx.x; c < n; c += blockDim.x)
+  {
+    const double f = cos(fx * pts[c * ld + 0]) * cos(fy * pts[c * ld + 1]);
+    acc += w ? f * w[c] : f;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1)
+  {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[k] = scale * red[0];
+}
+
+// Basis::gradFourierBasis (basis.cpp:91-107): dfk is 2 x K column-major
+__global__ void basis_grad_kernel(double lx, double ly, int nb, double x0, double x1, double* __restrict__ dfk)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nb * nb) return;
+  const double k1 = (double)(k % nb) * (kPi / lx), k2 = (double)(k / nb) * (kPi / ly);
+  dfk[2 * k + 0] = -k1 * sin(k1 * x0) * cos(k2 * x1);
+  dfk[2 * k + 1] = -k2 * cos(k1 * x0) * sin(k2 * x1);
+}
+
+// Target::fill over arbitrary points (target.cpp:78-89): un-normalised values,
+// then a single-CTA sum; the division happens in target_scale_kernel.
+__global__ void target_points_kernel(int ng, const double* __restrict__ gauss, const double* __restrict__ pts,
+                                     long long n, double* __restrict__ vals)
+{
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const double px = pts[2 * c], py = pts[2 * c + 1];
+  double val = 0.0;
+  for (int g = 0; g < ng; g++)
+  {
+    const double* G = gauss + 6 * g;
+    const double d0 = px - G[0], d1 = py - G[1];
+    const double r0 = d0 * G[2] + d1 * G[3];
+    const double r1 = d0 * G[4] + d1 * G[5];
+    val += exp(-0.5 * (r0 * d0 + r1 * d1));
+  }
+  vals[c] = val;
+}
+
+__global__ void __launch_bounds__(1024) vector_sum_kernel(const double* __restrict__ v, long long n,
+                                                          double* __restrict__ total)
+{
+  __shared__ double red[1024];
+  double acc = 0.0;
+  for (long long c = threadIdx.x; c < n; c += blockDim.x) acc += v[c];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1)
+  {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = red[0];
+}
+
+__global__ void vector_div_kernel(double* __restrict__ v, long long n, const double* __restrict__ total)
+{
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) v[c] /= *total;
+}
+
 // ---- FP64 throughput probes (roofline denominator) -------------------------
 __global__ void __launch_bounds__(256) dfma_probe(double* out, int iters, double seed)
 {

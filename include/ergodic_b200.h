@@ -188,6 +188,24 @@ eb_status eb_phik_from_grid_host(int device, const double *phi, int nx, int ny, 
                                  double lx, double ly, int nb, double *phik, double *phi_sum);
 long long eb_phik_launch_count(const eb_phik_plan *p);
 
+/* ---- stateless Basis / Target entry points on ARBITRARY points ----------
+ * (the public methods of the reference's Basis and Target classes; host
+ * buffers, computed on the device, synchronous)
+ * eb_basis_traj_coeff_host   Basis::trajCoeff (basis.cpp:109-120); xt is ld x ncols
+ *                            (ld = 2 or 3, only rows 0,1 are read).  With
+ *                            ncols = 1 this is Basis::fourierBasis (:79-89).
+ * eb_basis_grad_host         Basis::gradFourierBasis (:91-107); dfk is 2 x K
+ * eb_basis_spatial_coeff_host Basis::spatialCoeff (:122-133); phi_grid is 2 x G
+ * eb_target_fill_host        Target::fill (target.cpp:78-89): values at the
+ *                            points of phi_grid, normalised to sum to 1 */
+eb_status eb_basis_traj_coeff_host(int device, double lx, double ly, int nb, const double *xt, int ld,
+                                   int ncols, double *ck);
+eb_status eb_basis_grad_host(int device, double lx, double ly, int nb, const double *x, double *dfk);
+eb_status eb_basis_spatial_coeff_host(int device, double lx, double ly, int nb, const double *phi_vals,
+                                      const double *phi_grid, long long G, double *phik);
+eb_status eb_target_fill_host(int device, int ng, const double *mu, const double *sigma,
+                              const double *trans, const double *phi_grid, long long G, double *phi_vals);
+
 /* ---- measurement helper --------------------------------------------------
  * Measured FP64 throughput of the device (TFLOP/s, 2 flop per FMA): a
  * register-resident DFMA loop and an mma.sync m8n8k4 f64 (DMMA) loop.  Used
