@@ -51,6 +51,81 @@ __device__ __forceinline__ double warp_sum(double v)
   return v;
 }
 
+// ---- sin/cos kernels -------------------------------------------------------
+// Cody-Waite reduction to [-pi/4, pi/4] (two-term pi/2, exact to ~1e-33 * |q|)
+// followed by the fdlibm minimax kernels (|error| < 1 ulp).  About a third of
+// the instructions of the CUDA library sincos(), which carries a three-term
+// reduction, a Payne-Hanek slow path and special-value handling that the
+// bounded arguments of this kernel (headings, k*pi*x/l) never need; arguments
+// beyond 2^30 take the (out-of-line) library path.  The polynomial
+// coefficients live in constant memory so every DFMA reads them as a
+// constant-bank operand instead of materialising 64-bit immediates.
+__constant__ double kTrigS[6] = { -1.66666666666666324348e-01, 8.33333333332248946124e-03,
+                                  -1.98412698298579493134e-04, 2.75573137070700676789e-06,
+                                  -2.50507602534068634195e-08, 1.58969099521155010221e-10 };
+__constant__ double kTrigC[6] = { 4.16666666666666019037e-02, -1.38888888888741095749e-03,
+                                  2.48015872894767294178e-05, -2.75573143513906633035e-07,
+                                  2.08757232129817482790e-09, -1.13596475577881948265e-11 };
+__constant__ double kTrigR[5] = { 6.36619772367581382433e-01,   // 2/pi
+                                  1.57079632679489655800e+00,   // pi/2 hi
+                                  6.12323399573676603587e-17,   // pi/2 lo
+                                  3.14159265358979311600e+00,   // pi hi
+                                  1.22464679914735317723e-16 }; // pi lo
+
+__device__ __forceinline__ void sincos_kernel(double r, int n, double* s, double* c)
+{
+  const double z = r * r;
+  double ps = fma(z, kTrigS[5], kTrigS[4]);
+  double pc = fma(z, kTrigC[5], kTrigC[4]);
+  ps = fma(z, ps, kTrigS[3]);
+  pc = fma(z, pc, kTrigC[3]);
+  ps = fma(z, ps, kTrigS[2]);
+  pc = fma(z, pc, kTrigC[2]);
+  ps = fma(z, ps, kTrigS[1]);
+  pc = fma(z, pc, kTrigC[1]);
+  ps = fma(z, ps, kTrigS[0]);
+  pc = fma(z, pc, kTrigC[0]);
+  const double sn = fma(z * r, ps, r);                 // r + r^3 * P(r^2)
+  const double cs = 1.0 - fma(0.5, z, -(z * z) * pc);  // 1 - (z/2 - z^2 * Q(r^2))
+  // quadrant n: (sin, cos) = (sn, cs), (cs, -sn), (-sn, -cs), (-cs, sn); signs by
+  // flipping the sign bit of the high word
+  const bool swap = n & 1;
+  const double a = swap ? cs : sn, b = swap ? sn : cs;
+  const int sa = (n & 2) << 30, sb = ((n + 1) & 2) << 30;
+  *s = __hiloint2double(__double2hiint(a) ^ sa, __double2loint(a));
+  *c = __hiloint2double(__double2hiint(b) ^ sb, __double2loint(b));
+}
+
+__device__ __noinline__ void slow_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __noinline__ void slow_sincospi(double x, double* s, double* c) { sincospi(x, s, c); }
+
+__device__ __forceinline__ void fast_sincos(double x, double* s, double* c)
+{
+  if (fabs(x) > 1073741824.0)
+  {
+    slow_sincos(x, s, c);
+    return;
+  }
+  const double q = rint(x * kTrigR[0]);
+  double r = fma(-q, kTrigR[1], x);
+  r = fma(-q, kTrigR[2], r);
+  sincos_kernel(r, (int)q, s, c);
+}
+
+// sin(pi t), cos(pi t): the reduction t - q/2 is exact
+__device__ __forceinline__ void fast_sincospi(double t, double* s, double* c)
+{
+  if (fabs(t) > 1073741824.0)
+  {
+    slow_sincospi(t, s, c);
+    return;
+  }
+  const double q = rint(t + t);
+  const double f = fma(-0.5, q, t);  // exact, |f| <= 1/4
+  const double r = fma(f, kTrigR[3], f * kTrigR[4]);
+  sincos_kernel(r, (int)q, s, c);
+}
+
 // numerics.hpp:77-89
 __device__ __forceinline__ double normalize_angle_pi(double rad)
 {

@@ -24,7 +24,7 @@
 //  * the metric gradient is a pair of bilinear forms per step,
 //    sx^T (a.S) cy and cx^T (S.b) sy: each lane evaluates them for its own time
 //    step with S broadcast from shared memory, cos/sin rows held in registers.
-// Shared memory per warp: 2*NB*36 + 8*32*rounds doubles.
+// Shared memory per warp: 2*NB*20 + 8*32*rounds doubles.
 #pragma once
 
 #include "common.cuh"
@@ -34,7 +34,8 @@ namespace eb
 constexpr int kModelSimpleCart = 0;
 constexpr int kModelOmni = 1;
 constexpr int kSolveWarps = 4;   // warps (instances in flight) per CTA
-constexpr int kTabStride = 36;   // 32 time slots + 4 pad: 36 % 16 == 4 -> conflict-free fragment loads
+constexpr int kTabSlots = 16;    // time slots per coefficient chunk (half a round)
+constexpr int kTabStride = 20;   // 16 slots + 4 pad: 20 % 16 == 4 -> conflict-free fragment loads
 constexpr int kRecFields = 8;    // per-step record: c_th, s_th, xf, yf, c_a|ex, s_a|ey, c_b, s_b
 
 struct SolveParams
@@ -95,8 +96,8 @@ __device__ __forceinline__ void rollout_round(const double dt, const bool valid,
   tho = cy.th + inc;
   const double thm = th_before + dt * (0.5 * u2);  // k2, k3 stage heading
   double sm, cm;
-  sincos(tho, &se, &ce);  // k4 stage heading == post-step heading (to rounding)
-  sincos(thm, &sm, &cm);
+  fast_sincos(tho, &se, &ce);  // k4 stage heading == post-step heading (to rounding)
+  fast_sincos(thm, &sm, &cm);
   double cb = __shfl_up_sync(kFull, ce, 1), sb = __shfl_up_sync(kFull, se, 1);
   if (lane == 0)
   {
@@ -118,56 +119,74 @@ __device__ __forceinline__ void rollout_round(const double dt, const bool valid,
   cy.sth = __shfl_sync(kFull, se, 31);
 }
 
-// Rank-32 update of the nb x nb coefficient accumulators from one chunk of
-// (up to) 32 states: lanes write their Chebyshev cosine rows to shared memory
-// (transposed: tab[k][t]), then the warp runs nvalid/4 DMMA k-steps.
+// Rank-32 update of the nb x nb coefficient accumulators from one round of
+// (up to) 32 states, in two half-rounds of 16: the lanes of the half write
+// their Chebyshev cosine rows to shared memory (transposed: tab[k][slot]),
+// then the warp runs up to four DMMA k-steps over those 16 states.
 template <int NB>
 __device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, double* __restrict__ taby, const int lane,
                                             const bool valid, const int nvalid, const double c1x,
                                             const double c1y, double (&acc)[(NB + 7) / 8][(NB + 7) / 8][2])
 {
   constexpr int TILES = (NB + 7) / 8;
-  __syncwarp();
-  {
-    // T_k(c) by the three-term recurrence, started one step early:
-    // (T_{-1}, T_0) = (c, 1) so that the first advance yields T_1 = c.
-    double xm = c1x, xk = 1.0, ym = c1y, yk = 1.0;
-    const double tx = 2.0 * c1x, ty = 2.0 * c1y;
-#pragma unroll
-    for (int k = 0; k < NB; k++)
-    {
-      tabx[k * kTabStride + lane] = valid ? xk : 0.0;
-      taby[k * kTabStride + lane] = valid ? yk : 0.0;
-      const double xn = tx * xk - xm, yn = ty * yk - ym;
-      xm = xk;
-      xk = xn;
-      ym = yk;
-      yk = yn;
-    }
-  }
-  __syncwarp();
   const int g = lane >> 2, q = lane & 3;
-  const int ksteps = (nvalid + 3) >> 2;
-  for (int s = 0; s < ksteps; s++)
+#pragma unroll
+  for (int h = 0; h < 2; h++)
   {
-    double a[TILES], b[TILES];
-#pragma unroll
-    for (int t = 0; t < TILES; t++)
+    const int left = nvalid - h * kTabSlots;  // valid states in this half (warp-uniform)
+    if (left <= 0) break;
+    __syncwarp();
+    if ((lane >> 4) == h)
     {
-      const int k = 8 * t + g;
-      const bool in = (TILES * 8 == NB) || (k < NB);
-      a[t] = in ? taby[k * kTabStride + 4 * s + q] : 0.0;
-      b[t] = in ? tabx[k * kTabStride + 4 * s + q] : 0.0;
+      // T_k(c) by the three-term recurrence, started one step early:
+      // (T_{-1}, T_0) = (c, 1) so that the first advance yields T_1 = c.
+      // Lanes past the end of the trajectory write zero rows (c = 0, T_0 = 0).
+      const int slot = lane & 15;
+      const double vx = valid ? c1x : 0.0, vy = valid ? c1y : 0.0;
+      double xm = vx, xk = valid ? 1.0 : 0.0, ym = vy, yk = xk;
+      const double tx = 2.0 * vx, ty = 2.0 * vy;
+#pragma unroll
+      for (int k = 0; k < NB; k++)
+      {
+        tabx[k * kTabStride + slot] = xk;
+        taby[k * kTabStride + slot] = yk;
+        const double xn = tx * xk - xm, yn = ty * yk - ym;
+        xm = xk;
+        xk = xn;
+        ym = yk;
+        yk = yn;
+      }
     }
+    __syncwarp();
+    const int ksteps = (min(left, kTabSlots) + 3) >> 2;
+    for (int s = 0; s < ksteps; s++)
+    {
+      double a[TILES], b[TILES];
 #pragma unroll
-    for (int ti = 0; ti < TILES; ti++)
+      for (int t = 0; t < TILES; t++)
+      {
+        const int k = 8 * t + g;
+        const bool in = (TILES * 8 == NB) || (k < NB);
+        a[t] = in ? taby[k * kTabStride + 4 * s + q] : 0.0;
+        b[t] = in ? tabx[k * kTabStride + 4 * s + q] : 0.0;
+      }
 #pragma unroll
-      for (int tj = 0; tj < TILES; tj++) dmma884(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
+      for (int ti = 0; ti < TILES; ti++)
+#pragma unroll
+        for (int tj = 0; tj < TILES; tj++) dmma884(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
+    }
   }
 }
 
+// resident CTAs per SM the register allocation is tuned for (4 warps per CTA)
+template <int NB>
+constexpr int solve_min_blocks()
+{
+  return NB <= 10 ? 7 : NB <= 16 ? 5 : NB <= 24 ? 3 : 2;
+}
+
 template <int MODEL, int NB>
-__global__ void __launch_bounds__(kSolveWarps * 32) solve_kernel(const SolveParams p)
+__global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solve_kernel(const SolveParams p)
 {
   constexpr int TILES = (NB + 7) / 8;
   extern __shared__ double smem[];
@@ -192,7 +211,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) solve_kernel(const SolvePara
   double* tabx = smem + 2 * NB * NB + warp * (2 * NB * kTabStride + kRecFields * npad);
   double* taby = tabx + NB * kTabStride;
   double* rec = taby + NB * kTabStride;
-  double* Ssm = tabx;  // S aliases the x table once c_k is complete
+  double* Ssm = tabx;  // S (NB x NB) aliases the two tables (2*NB*20 doubles) once c_k is complete
 
   double acc[TILES][TILES][2];
 #pragma unroll
@@ -220,8 +239,9 @@ __global__ void __launch_bounds__(kSolveWarps * 32) solve_kernel(const SolvePara
       if (p.idx_mode != 0 && p.mem_idx_out) p.mem_idx_out[(size_t)inst * p.batch_size + j] = (int)idx;
       const double* h = p.hist + ((size_t)idx * p.B + inst) * 3;
       const double xf = h[0] - p.xmin, yf = h[1] - p.ymin;
-      c1x = cospi(xf * p.inv_lx);
-      c1y = cospi(yf * p.inv_ly);
+      double sdummy;
+      fast_sincospi(xf * p.inv_lx, &sdummy, &c1x);
+      fast_sincospi(yf * p.inv_ly, &sdummy, &c1y);
     }
     const int nvalid = min(32, p.M - base);
     coeff_chunk<NB>(tabx, taby, lane, valid, nvalid, c1x, c1y, acc);
@@ -236,7 +256,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) solve_kernel(const SolvePara
     cy.x = x0[0];
     cy.y = x0[1];
     cy.th = x0[2];
-    sincos(cy.th, &cy.sth, &cy.cth);
+    fast_sincos(cy.th, &cy.sth, &cy.cth);
   }
   for (int r = 0; r < rounds; r++)
   {
@@ -254,8 +274,8 @@ __global__ void __launch_bounds__(kSolveWarps * 32) solve_kernel(const SolvePara
     rollout_round<MODEL>(p.dt, valid, lane, u0, u1, u2, cy, xo, yo, tho, ce, se);
     const double xf = xo - p.xmin, yf = yo - p.ymin;
     double ca, sa, cb, sb;
-    sincospi(xf * p.inv_lx, &sa, &ca);
-    sincospi(yf * p.inv_ly, &sb, &cb);
+    fast_sincospi(xf * p.inv_lx, &sa, &ca);
+    fast_sincospi(yf * p.inv_ly, &sb, &cb);
     rec[0 * npad + i] = ce;
     rec[1 * npad + i] = se;
     rec[2 * npad + i] = xf;
@@ -465,7 +485,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(int B, int N, double dt, c
   cy.x = pose[(size_t)inst * 3 + 0];
   cy.y = pose[(size_t)inst * 3 + 1];
   cy.th = pose[(size_t)inst * 3 + 2];
-  sincos(cy.th, &cy.sth, &cy.cth);
+  fast_sincos(cy.th, &cy.sth, &cy.cth);
   for (int base = 0; base < N; base += 32)
   {
     const int i = base + lane;
