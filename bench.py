@@ -41,6 +41,8 @@ WORKLOADS = {
     # name: model, nb, horizon, batch per GPU, memory states, description
     "c2": dict(model=1, nb=10, horizon=5.0, batch=4096, mem=0,
                desc="configs[1]: Omni, 10x10 basis, 4096 instances, 50-step horizon"),
+    "c2big": dict(model=1, nb=10, horizon=5.0, batch=262144, mem=0,
+                  desc="configs[1] shape at 64x the batch: Omni, 10x10 basis, 262144 instances, 50-step horizon"),
     "c4": dict(model=0, nb=20, horizon=10.0, batch=131072, mem=0,
                desc="configs[3] shard: SimpleCart, 20x20 basis, 131072 instances/GPU, 100-step horizon"),
     "c5": dict(model=1, nb=16, horizon=5.0, batch=65536, mem=100,
@@ -243,18 +245,42 @@ def run_ours(args, wl, rank, world, local_rank):
     M = min(wl["mem"], 100)
 
     xd = torch.from_numpy(x).to(dev)
-    u0d = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    u0bufs = [torch.empty((B, 3), dtype=torch.float64, device=dev) for _ in range(2)]
+    u0d = u0bufs[0]
     metd = torch.empty(B, dtype=torch.float64, device=dev)
     gathered = torch.empty((world * B, 3), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    state = {"i": 0, "gather_done": None}
 
     def step_dev():
-        ctl.control(BOUNDS, xd, u0=u0d, metric=metd)
+        """one control() over this rank's instances; for N > 1 the all_gather of
+        step i runs on a side stream and overlaps step i+1's kernel (the ranks
+        own their instances, nothing in the next step depends on the gather);
+        step i+1 does not finish before gather i has."""
+        buf = u0bufs[state["i"] & 1]
+        state["i"] += 1
+        ctl.control(BOUNDS, xd, u0=buf, metric=metd)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, u0d)
+            main = torch.cuda.current_stream()
+            kdone = torch.cuda.Event()
+            kdone.record(main)
+            if state["gather_done"] is not None:
+                main.wait_event(state["gather_done"])
+            with torch.cuda.stream(side):
+                side.wait_event(kdone)
+                dist.all_gather_into_tensor(gathered, buf)
+                state["gather_done"] = torch.cuda.Event()
+                state["gather_done"].record(side)
+
+    def drain():
+        if world > 1 and state["gather_done"] is not None:
+            torch.cuda.current_stream().wait_event(state["gather_done"])
+            state["gather_done"] = None
 
     for _ in range(max(3, args.warmup)):
         step_dev()
+    drain()
     ctl.check()
     torch.cuda.synchronize()
 
@@ -265,13 +291,16 @@ def run_ours(args, wl, rank, world, local_rank):
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = ctl.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     wall0 = time.perf_counter()
-    for a, b in ev:
+    for a, b in ev[:-1]:
         flush.zero_()  # evict the previous step's ut_/x from L2 (outside the event pair)
         a.record()
         step_dev()
         b.record()
+    ev[-1][0].record()
+    drain()  # the last gather's tail is part of the job
+    ev[-1][1].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -343,7 +372,8 @@ def run_ours(args, wl, rank, world, local_rank):
         "config": {"workload": wl["desc"], "instances_per_gpu": B, "num_basis": wl["nb"], "horizon_steps": N,
                    "replay_states": M, "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
                    "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks",
-                   "parallelism": f"instances sharded over {world} GPU(s), all_gather of u0 per step" if world > 1
+                   "parallelism": f"instances sharded over {world} GPU(s), one NCCL all_gather of u0 per step on a side "
+                                  f"stream (overlaps the next step's kernel)" if world > 1
                    else "single GPU"},
         "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
         "e2e": {"value": world * B * args.steps / e2e_s, "unit": "solves/s",

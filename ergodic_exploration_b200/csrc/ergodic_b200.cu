@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -332,7 +333,8 @@ struct eb_controller
   long long hist_cap = 0, mem_count = 0;
   double *d_phik = nullptr, *d_lamk = nullptr;
   double *d_u0 = nullptr, *d_metric = nullptr, *d_ck = nullptr, *d_x = nullptr;
-  int *d_mem_idx_in = nullptr, *d_mem_idx_out = nullptr, *d_fault = nullptr;
+  int *d_mem_idx_in = nullptr, *d_mem_idx_out = nullptr;
+  int *h_fault = nullptr, *d_fault = nullptr;  // pinned + mapped: the kernels set it, the host reads it after a sync
   int last_idx_count = 0;
   double lx = 0.0, ly = 0.0;  // basis_.lx_, basis_.ly_ (0, 0 at construction :208)
   double map_pos[2] = { 0.0, 0.0 };
@@ -405,12 +407,10 @@ eb_status ensure_hist(eb_controller* c, long long need)
 
 eb_status check_fault(eb_controller* c)
 {
-  int f = 0;
-  EB_CUDA(cudaMemcpyAsync(&f, c->d_fault, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   EB_CUDA(cudaStreamSynchronize(c->stream));
-  if (f)
+  if (*static_cast<volatile int*>(c->h_fault))
   {
-    EB_CUDA(cudaMemsetAsync(c->d_fault, 0, sizeof(int), c->stream));
+    *c->h_fault = 0;
     return fail(EB_ERR_INVALID_ARGUMENT, "Invalid twist y-velocity must be 0.");  // cart.hpp:169
   }
   return EB_OK;
@@ -476,8 +476,9 @@ eb_status eb_create(const eb_config* cfg, eb_controller** out)
   EB_CUDA_C(cudaMalloc(&c->d_lamk, sizeof(double) * c->K));
   EB_CUDA_C(cudaMalloc(&c->d_mem_idx_in, sizeof(int) * (size_t)std::max(1u, cfg->batch_size) * c->B));
   EB_CUDA_C(cudaMalloc(&c->d_mem_idx_out, sizeof(int) * (size_t)std::max(1u, cfg->batch_size) * c->B));
-  EB_CUDA_C(cudaMalloc(&c->d_fault, sizeof(int)));
-  EB_CUDA_C(cudaMemset(c->d_fault, 0, sizeof(int)));
+  EB_CUDA_C(cudaHostAlloc(&c->h_fault, sizeof(int), cudaHostAllocMapped));
+  *c->h_fault = 0;
+  EB_CUDA_C(cudaHostGetDevicePointer(&c->d_fault, c->h_fault, 0));
   // Basis::Basis (basis.cpp:48-77): index = ky*nb + kx, lamda_k = 1/(1+sqrt(kx^2+ky^2))^1.5
   std::vector<double> lam(c->K);
   for (int ky = 0; ky < c->nb; ky++)
@@ -505,7 +506,7 @@ void eb_destroy(eb_controller* c)
   cudaFree(c->d_x);
   cudaFree(c->d_mem_idx_in);
   cudaFree(c->d_mem_idx_out);
-  cudaFree(c->d_fault);
+  cudaFreeHost(c->h_fault);
   cudaFree(c->d_phi_grid);
   cudaFree(c->d_gauss);
   eb_phik_plan_destroy(c->plan);
@@ -708,9 +709,7 @@ eb_status eb_control_dev(eb_controller* c, double xmin, double xmax, double ymin
   eb_status st = eb_config_target(c, xmin, xmax, ymin, ymax, nullptr);  // :230
   if (st != EB_OK) return st;
   // pose_ = x (:227)
-  if (x_dev != c->d_pose)
-    EB_CUDA(cudaMemcpyAsync(c->d_pose, x_dev, sizeof(double) * 3 * c->B, cudaMemcpyDeviceToDevice, c->stream));
-  c->have_pose = true;
+  c->have_pose = true;  // the kernel records x as pose_ (for optTraj)
 
   eb::SolveParams p{};
   p.B = c->B;
@@ -749,7 +748,8 @@ eb_status eb_control_dev(eb_controller* c, double xmin, double xmax, double ymin
   p.beps = c->cfg.barrier_eps;
   p.seed = c->cfg.seed;
   p.call = c->call++;
-  p.x = c->d_pose;
+  p.x = x_dev;
+  p.pose_out = (x_dev != c->d_pose) ? c->d_pose : nullptr;
   p.ut_in = c->d_ut[c->cur];
   p.ut_out = c->d_ut[c->cur ^ 1];
   p.hist = c->d_hist;

@@ -46,6 +46,7 @@ struct SolveParams
   double Rinv[9], umin[3], umax[3], bw, beps;
   unsigned long long seed, call;
   const double* x;       // [B][3]
+  double* pose_out;      // [B][3] or null: copy of x kept as pose_ (:227)
   const double* ut_in;   // [B][N][3]
   double* ut_out;        // [B][N][3]
   const double* hist;    // [cap][B][3]
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
     cy.x = x0[0];
     cy.y = x0[1];
     cy.th = x0[2];
+    if (p.pose_out && lane < 3) p.pose_out[(size_t)inst * 3 + lane] = x0[lane];
     fast_sincos(cy.th, &cy.sth, &cy.cth);
   }
   for (int r = 0; r < rounds; r++)
