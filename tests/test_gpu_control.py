@@ -254,3 +254,114 @@ def test_device_path_matches_host_path():
     b.check()
     np.testing.assert_array_equal(u_host, ud.cpu().numpy())
     assert b.launch_count() >= 1
+
+
+@pytest.mark.parametrize("nb", [1, 2, 3, 5, 8, 9, 13, 17, 21, 25, 31])
+def test_every_basis_count_path(nb):
+    """num_basis values between the instantiated tile sizes run on the next
+    larger instantiation with the extra coefficients masked"""
+    rng = np.random.default_rng(100 + nb)
+    B, model = 5, MODEL_OMNI if nb % 2 else MODEL_SIMPLE_CART
+    gpu = make_gpu(model, B, nb=nb, horizon=3.0)
+    orcs = [make_oracle(model, nb=nb, horizon=3.0) for _ in range(B)]
+    x = random_states(rng, B)
+    ut = warm_ut(rng, B, gpu.steps, model)
+    gpu.set_ut(ut)
+    for i, o in enumerate(orcs):
+        o.set_ut(ut[i])
+    for past in (random_states(rng, B) for _ in range(7)):
+        gpu.addStateMemory(past)
+        for i, o in enumerate(orcs):
+            o.add_state_memory(past[i])
+    _compare_step(gpu, orcs, BOUNDS_10, x, tag=f"nb={nb}")
+
+
+def test_long_horizon_many_rounds():
+    """200 horizon steps = 7 rounds of 32 time-step lanes"""
+    rng = np.random.default_rng(77)
+    B, model = 3, MODEL_OMNI
+    gpu = make_gpu(model, B, nb=6, horizon=20.0)
+    orcs = [make_oracle(model, nb=6, horizon=20.0) for _ in range(B)]
+    assert gpu.steps == 200
+    x = random_states(rng, B)
+    ut = warm_ut(rng, B, gpu.steps, model) * 0.3
+    gpu.set_ut(ut)
+    for i, o in enumerate(orcs):
+        o.set_ut(ut[i])
+    _compare_step(gpu, orcs, BOUNDS_10, x, tag="N=200")
+
+
+def test_other_dt_weights_and_limits():
+    """non-default dt, exploration weight, control weights and limits"""
+    import ergodic_exploration_b200 as eb
+    from oracle.pyoracle import Oracle
+
+    rng = np.random.default_rng(21)
+    B = 6
+    R = np.array([[0.7, 0.1, 0.0], [0.05, 1.3, 0.02], [0.0, 0.3, 2.5]])  # a full (non-diagonal) Rinv
+    umin, umax = np.array([-0.4, -0.6, -1.1]), np.array([0.9, 0.3, 0.8])
+    mu, sg = [[1.0, 3.0], [4.5, 1.5], [2.0, 2.0]], [[0.4, 0.9], [1.2, 0.3], [0.7, 0.7]]
+    bounds = (-2.0, 4.0, 0.5, 4.5)
+    gpu = eb.ErgodicControl(eb.Omni(), 0.05, 1.35, 0.07, 3.5, 9, 500, 20, R, umin, umax, batch=B)
+    gpu.setTarget([eb.Gaussian(m, s) for m, s in zip(mu, sg)])
+    orcs = []
+    for _ in range(B):
+        o = Oracle.create(MODEL_OMNI, 0.05, 1.35, 0.07, 3.5, 9, 500, 20, R, umin, umax)
+        o.set_target(mu, sg)
+        orcs.append(o)
+    assert gpu.steps == orcs[0].steps == 27
+    x = random_states(rng, B, bounds=bounds, margin=0.2)
+    ut = rng.uniform(umin, umax, size=(B, gpu.steps, 3))
+    gpu.set_ut(ut)
+    for i, o in enumerate(orcs):
+        o.set_ut(ut[i])
+    for step in range(3):
+        u0 = _compare_step(gpu, orcs, bounds, x, tag=f"custom step {step}")
+        gpu.set_ut(np.stack([o.get_ut() for o in orcs]))
+        x = plant(x, u0, dt=0.05)
+        gpu.addStateMemory(x)
+        for i, o in enumerate(orcs):
+            o.add_state_memory(x[i])
+
+
+def test_memory_buffer_drops_when_full():
+    """ReplayBuffer::append silently drops states once buffer_size are stored (buffer.cpp:56-61)"""
+    rng = np.random.default_rng(31)
+    B = 2
+    gpu = make_gpu(MODEL_OMNI, B, buffer_size=5, batch_size=100)
+    orcs = [make_oracle(MODEL_OMNI, buffer_size=5, batch_size=100) for _ in range(B)]
+    for _ in range(9):
+        past = random_states(rng, B)
+        gpu.addStateMemory(past)
+        for i, o in enumerate(orcs):
+            o.add_state_memory(past[i])
+    assert gpu.memory_size() == 5 and orcs[0].memory_size() == 5
+    _compare_step(gpu, orcs, BOUNDS_10, random_states(rng, B), tag="full buffer")
+
+
+def test_large_batch_properties():
+    """BASELINE-size batch (no oracle at this size): finite, within limits,
+    duplicated instances give identical rows, metric >= 0"""
+    import torch
+
+    rng = np.random.default_rng(41)
+    B, model = 1 << 16, MODEL_OMNI
+    gpu = make_gpu(model, B, nb=16)
+    x = random_states(rng, B)
+    x[B // 2:] = x[: B // 2]  # second half duplicates the first
+    ut = warm_ut(rng, B // 2, 50, model)
+    gpu.set_ut(np.concatenate([ut, ut]))
+    xd = torch.from_numpy(x).cuda()
+    md = torch.empty(B, dtype=torch.float64, device="cuda")
+    u = gpu.control(BOUNDS_10, xd, metric=md).cpu().numpy()
+    gpu.check()
+    m = md.cpu().numpy()
+    assert np.isfinite(u).all() and np.isfinite(m).all() and (m >= 0).all()
+    assert (np.abs(u[:, 0]) <= 1).all() and (np.abs(u[:, 1]) <= 1).all() and (np.abs(u[:, 2]) <= 2).all()
+    np.testing.assert_array_equal(u[: B // 2], u[B // 2:])
+    np.testing.assert_array_equal(m[: B // 2], m[B // 2:])
+    # a sample of rows against the oracle
+    for i in rng.integers(0, B // 2, 6):
+        o = make_oracle(model, nb=16)
+        o.set_ut(ut[i])
+        assert_abs_rel_close(u[i], o.control(BOUNDS_10, x[i]), f"row {i}")
