@@ -424,6 +424,8 @@ def run_phik(args, rank, world, local_rank):
     for _ in range(max(3, args.warmup)):
         plan.execute(phi, out)
     torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     l0 = plan.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in ev:
@@ -431,6 +433,7 @@ def run_phik(args, rank, world, local_rank):
         plan.execute(phi, out)
         b.record()
     torch.cuda.synchronize()
+    clk = clocks.stop()
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     dfma, dmma = eb.fp64_peak(local_rank)
     flops = 2.0 * nx * ny * nb + 2.0 * ny * nb * nb
@@ -446,7 +449,7 @@ def run_phik(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[2]: phi_k over 8192x8192 Gaussian-mixture grid, 32x32 basis",
                    "l2": "input (512 MiB) larger than L2"},
-        "gpu_launches": int(plan.launch_count() - l0),
+        "gpu_launches": int(plan.launch_count() - l0), "clocks": clk,
         "roofline": {"kernel": "phik contraction", "bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12,
                      "peak": max(dfma, dmma), "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / max(dfma, dmma),
                      "traffic": None,

@@ -10,15 +10,16 @@
 // 64-column half of every chunk:
 //     T[8 rows][32 kx] += Phi[8 rows][4 cols] * C_x[4 cols][32 kx]      (DMMA m8n8k4 x 4)
 //  * Phi is streamed straight from HBM into the A fragments: each lane keeps a
-//    rotating window of four 32-byte loads in flight (64 KB per SM), a quad
-//    reads 128 contiguous bytes per row, every sector is used exactly once.
+//    register double buffer of four 32-byte loads per chunk (64 KB in flight
+//    per SM, issued a whole chunk ahead); a quad reads 128 contiguous bytes per
+//    row, every sector is used exactly once.
 //  * the C_x chunk (128 columns x 32 bases, 36 KB with the conflict-free row
 //    pitch of 36 doubles) is staged in shared memory by the TMA bulk-copy engine
 //    (cp.async.bulk -> UBLKCP) into a three-stage ring with full/empty
 //    mbarriers, issued by a dedicated producer warp, so the consumer warps never
 //    meet at a CTA barrier inside a unit; the chunk rows are stored pre-permuted
 //    so the B-fragment loads are bank-conflict free.  The producer warp also
-//    runs cp.async.bulk.prefetch.L2 over the Phi rows six chunk iterations
+//    runs cp.async.bulk.prefetch.L2 over the Phi rows two chunk iterations
 //    ahead, so the register window is refilled at L2 latency, not HBM latency.
 //  * at the end of a unit the two column halves' tiles are summed in a
 //    64 x 32 shared-memory stage and the CTA folds it into its running 32 x 32
@@ -27,6 +28,8 @@
 // Every CTA writes one 32 x 32 partial; phik_finalize sums them in a fixed
 // order (deterministic) and normalises by P[0][0] = sum(Phi).
 #pragma once
+
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -38,7 +41,7 @@ constexpr int kPdPitch = 36;        // doubles per chunk row: 36*8 B = 288 = 32 
 constexpr int kPdWarps = 16;        // consumer warps: 8 row groups x 2 column halves of every chunk
 constexpr int kPdThreads = (kPdWarps + 1) * 32;  // + 1 producer warp (TMA issue, L2 prefetch of Phi)
 constexpr int kPdStages = 3;        // C_x ring depth
-constexpr int kPdAhead = 6;         // Phi is prefetched into L2 this many chunk iterations ahead
+constexpr int kPdAhead = 2;         // Phi is prefetched into L2 this many chunk iterations ahead
 constexpr int kPdChunkBytes = kPdChunk * kPdPitch * 8;  // 36864
 constexpr int kPdStagePitch = 33;
 constexpr int kPdSmemBytes = kPdStages * kPdChunkBytes + kPdRows * kPdStagePitch * 8 + 128;
@@ -110,8 +113,10 @@ __device__ __forceinline__ void ldg_stream4(const double* p, bool pred, double (
 {
   if (pred)
   {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "l"(p + 2));
+    // one 256-bit load (sm_100+): a quad covers a full 128-byte line per row
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+                 : "l"(p));
   }
   else
     v[0] = v[1] = v[2] = v[3] = 0.0;
@@ -123,7 +128,7 @@ struct PhikDmmaParams
   const double* cxp;   // permuted C_x, [nchunks*128][36]
   const double* cy;    // C_y, [ny][32]
   double* parts;       // [gridDim.x][1024]
-  int nx, ny, nchunks, span, nspans, nunits;
+  int nx, ny, nchunks, span, nspans, nunits, ahead;
 };
 
 // iteration cursor: unit id + chunk index inside the unit, advanced without divisions
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmma
       pf_cur.advance(p, (int)gridDim.x);
       pf_it++;
     };
-    while (pf_it < min(kPdAhead, total_it)) prefetch_phi();
+    while (pf_it < min(p.ahead, total_it)) prefetch_phi();
     for (int it = 0; it < total_it; it++)
     {
       const int s = it % kPdStages;
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmma
                      kPdChunkBytes, &full[s]);
       }
       cx_cur.advance(p, (int)gridDim.x);
-      if (pf_it < total_it) prefetch_phi();
+      if (p.ahead > 0 && pf_it < total_it) prefetch_phi();
     }
     return;
   }
@@ -227,20 +232,22 @@ __global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmma
   ld_cur.init(p, (int)blockIdx.x);
   int cur_rb = ld_cur.rb;
 
-  double v[4][4];  // rotating window of Phi loads: 16-column group grp of the current / next chunk
+  // Phi fragments are double-buffered in registers: the 32-byte loads of chunk
+  // it + 1 are all issued BEFORE the DMMAs of chunk it (ptxas otherwise sinks
+  // them behind the last use of a shared window and exposes the full latency).
+  double va[4][4], vb[4][4];
   if (total_it > 0)
   {
     const int row = ld_cur.rb * kPdRows + rg * 8 + g, col0 = ld_cur.chunk(p) * kPdChunk + half * 64;
     const double* src = p.phi + (size_t)row * p.nx + col0 + 4 * q;
 #pragma unroll
     for (int grp = 0; grp < 4; grp++)
-      ldg_stream4(src + 16 * grp, row < p.ny && col0 + 16 * grp + 4 * q < p.nx, v[grp]);
+      ldg_stream4(src + 16 * grp, row < p.ny && col0 + 16 * grp + 4 * q < p.nx, va[grp]);
     ld_cur.advance(p, (int)gridDim.x);
   }
 
   int k_in_unit = 0;
-  for (int it = 0; it < total_it; it++)
-  {
+  auto iteration = [&](const int it, double (&vc)[4][4], double (&vn)[4][4]) {
     const int s = it % kPdStages;
     const bool has_next = it + 1 < total_it;
     const int nrow = ld_cur.rb * kPdRows + rg * 8 + g, ncol0 = ld_cur.chunk(p) * kPdChunk + half * 64;
@@ -248,23 +255,22 @@ __global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmma
     const double* nsrc = p.phi + (size_t)nrow * p.nx + ncol0 + 4 * q;
     const bool nrow_ok = has_next && nrow < p.ny;
     if (has_next) ld_cur.advance(p, (int)gridDim.x);
+#pragma unroll
+    for (int grp = 0; grp < 4; grp++)
+      ldg_stream4(nsrc + 16 * grp, nrow_ok && ncol0 + 16 * grp + 4 * q < p.nx, vn[grp]);
 
     mbar_wait(&full[s], (it / kPdStages) & 1);
     const double* bbase = cxs0 + s * (kPdChunkBytes / 8) + (half * 64 + q) * kPdPitch + g;
 #pragma unroll
     for (int grp = 0; grp < 4; grp++)
-    {
 #pragma unroll
       for (int st = 0; st < 4; st++)
       {
-        const double a = v[grp][st];
+        const double a = vc[grp][st];
         const double* brow = bbase + (16 * grp + 4 * st) * kPdPitch;
 #pragma unroll
         for (int t = 0; t < 4; t++) dmma884(T[t][0], T[t][1], a, brow[8 * t]);
       }
-      // refill this slot with the same group of the next chunk
-      ldg_stream4(nsrc + 16 * grp, nrow_ok && ncol0 + 16 * grp + 4 * q < p.nx, v[grp]);
-    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the C_x stage
 
@@ -311,6 +317,11 @@ __global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmma
       cur_rb = next_rb;
       consumer_barrier();  // the T stage may be overwritten by the next unit
     }
+  };
+  for (int it = 0; it < total_it; it += 2)
+  {
+    iteration(it, va, vb);
+    if (it + 1 < total_it) iteration(it + 1, vb, va);
   }
 
   {
@@ -335,6 +346,10 @@ inline int phik_dmma_launch(const double* phi, int nx, int ny, const double* cxp
   p.nx = nx;
   p.ny = ny;
   p.nchunks = (nx + kPdChunk - 1) / kPdChunk;
+  {
+    static const int ahead = getenv("EB_PHIK_AHEAD") ? atoi(getenv("EB_PHIK_AHEAD")) : kPdAhead;
+    p.ahead = ahead;
+  }
   const int row_blocks = (ny + kPdRows - 1) / kPdRows;
   const int grid_max = max_parts;
   double best = -1.0;
