@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libergodic_b200.so")
+LIB_PATH = os.environ.get("EB_LIB_PATH") or os.path.join(_HERE, "libergodic_b200.so")  # override: debug builds
 
 EB_OK = 0
 EB_ERR_INVALID_ARGUMENT = 1
@@ -89,6 +89,7 @@ SIGNATURES = {
     "eb_get_last_mem_idx": (C.c_int, [_vp, _vp, _ip]),
     "eb_ut_dev": (_vp, [_vp]),
     "eb_ck_dev": (_vp, [_vp]),
+    "eb_set_keep_ck": (C.c_int, [_vp, C.c_int]),
     "eb_launch_count": (C.c_longlong, [_vp]),
     "eb_phik_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                       C.POINTER(_vp)]),

@@ -231,6 +231,10 @@ class ErgodicControl:
         ut = _np_f64(ut).reshape(self.batch, self.steps, 3)
         check(self._lib.eb_set_ut(self._h, ut.ctypes.data))
 
+    def keep_ck(self, keep: bool) -> None:
+        """store (default) or skip the per-instance c_k by-product of control()"""
+        check(self._lib.eb_set_keep_ck(self._h, int(bool(keep))))
+
     def get_ck(self) -> np.ndarray:
         ck = np.empty((self.batch, self.num_coeff))
         check(self._lib.eb_get_ck(self._h, ck.ctypes.data))

@@ -347,7 +347,31 @@ struct eb_controller
   unsigned long long call = 0;
   long long launches = 0;
   bool have_pose = false;
+  bool keep_ck = true;  // store the c_k by-product of every control() (eb_get_ck)
+
+  // device alias of a page-locked host buffer (nullptr for pageable memory);
+  // looked up on every call -- a cached answer could outlive the allocation
+  static double* mapped(const void* host)
+  {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return (a.type == cudaMemoryTypeHost && a.devicePointer) ? static_cast<double*>(a.devicePointer) : nullptr;
+  }
 };
+
+// batches up to this size take the zero-copy host path (EB_ZEROCOPY_MAX_BATCH overrides; 0 disables)
+inline int zero_copy_max_batch()
+{
+  static const int v = [] {
+    const char* e = std::getenv("EB_ZEROCOPY_MAX_BATCH");
+    return e ? std::atoi(e) : 16384;
+  }();
+  return v;
+}
 
 namespace
 {
@@ -556,6 +580,7 @@ eb_status eb_clone(const eb_controller* src, eb_controller** out)
   c->gauss_sigma = src->gauss_sigma;
   c->call = src->call;
   c->have_pose = src->have_pose;
+  c->keep_ck = src->keep_ck;
   c->stream = src->stream;
   *out = c;
   return EB_OK;
@@ -577,6 +602,13 @@ long long eb_memory_size(const eb_controller* c) { return c ? c->mem_count : 0; 
 long long eb_launch_count(const eb_controller* c) { return c ? c->launches + (c->plan ? c->plan->launches : 0) : 0; }
 double* eb_ut_dev(eb_controller* c) { return c ? c->d_ut[c->cur] : nullptr; }
 double* eb_ck_dev(eb_controller* c) { return c ? c->d_ck : nullptr; }
+
+eb_status eb_set_keep_ck(eb_controller* c, int keep)
+{
+  if (!c) return fail(EB_ERR_INVALID_ARGUMENT, "controller is NULL");
+  c->keep_ck = keep != 0;
+  return EB_OK;
+}
 
 eb_status eb_set_target_gaussians(eb_controller* c, int n, const double* mu, const double* sigma)
 {
@@ -759,7 +791,7 @@ eb_status eb_control_dev(eb_controller* c, double xmin, double xmax, double ymin
   p.lamk = c->d_lamk;
   p.u0 = u0_dev;
   p.metric = metric_dev;
-  p.ck = c->d_ck;
+  p.ck = c->keep_ck ? c->d_ck : nullptr;
   p.fault = c->d_fault;
   const int rounds = (c->N + 31) / 32;
   cudaError_t e = launch_solve(p, c->cfg.model, rounds, c->stream);
@@ -768,6 +800,14 @@ eb_status eb_control_dev(eb_controller* c, double xmin, double xmax, double ymin
   c->cur ^= 1;
   return EB_OK;
 }
+
+#ifdef EB_PHASE_TIMING
+// debug build only (tools/phase_timing.py): copies the clock64() stamps of the last solve
+extern "C" int eb_debug_phase_dump(long long* host, int n)
+{
+  return (int)cudaMemcpyFromSymbol(host, eb::g_phase, sizeof(long long) * eb::kPhaseSlots * (size_t)n);
+}
+#endif
 
 eb_status eb_check_status(eb_controller* c)
 {
@@ -781,11 +821,26 @@ eb_status eb_control_host(eb_controller* c, double xmin, double xmax, double ymi
 {
   if (!c || !x || !u0) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_host: NULL argument");
   EB_CUDA(cudaSetDevice(c->cfg.device));
-  EB_CUDA(cudaMemcpyAsync(c->d_pose, x, sizeof(double) * 3 * c->B, cudaMemcpyHostToDevice, c->stream));
   const bool need_idx = mem_idx && c->mem_count > (long long)c->cfg.batch_size;
   if (need_idx)
     EB_CUDA(cudaMemcpyAsync(c->d_mem_idx_in, mem_idx, sizeof(int) * (size_t)c->cfg.batch_size * c->B,
                             cudaMemcpyHostToDevice, c->stream));
+  // Small batches with page-locked caller buffers: the kernel reads x and writes
+  // u0 / metric in place over PCIe (one launch + one sync, no copy-engine hops).
+  double *xm = nullptr, *um = nullptr, *mm = nullptr;
+  if (c->B <= zero_copy_max_batch())
+  {
+    xm = c->mapped(x);
+    um = xm ? c->mapped(u0) : nullptr;
+    mm = (um && metric) ? c->mapped(metric) : nullptr;
+  }
+  if (xm && um && (!metric || mm))
+  {
+    eb_status st = eb_control_dev(c, xmin, xmax, ymin, ymax, xm, need_idx ? c->d_mem_idx_in : nullptr, um, mm);
+    if (st != EB_OK) return st;
+    return check_fault(c);  // synchronises
+  }
+  EB_CUDA(cudaMemcpyAsync(c->d_pose, x, sizeof(double) * 3 * c->B, cudaMemcpyHostToDevice, c->stream));
   eb_status st = eb_control_dev(c, xmin, xmax, ymin, ymax, c->d_pose, need_idx ? c->d_mem_idx_in : nullptr, c->d_u0,
                                 metric ? c->d_metric : nullptr);
   if (st != EB_OK) return st;
@@ -852,6 +907,7 @@ eb_status eb_set_ut(eb_controller* c, const double* ut)
 eb_status eb_get_ck(const eb_controller* c, double* ck)
 {
   if (!c || !ck) return fail(EB_ERR_INVALID_ARGUMENT, "eb_get_ck: NULL argument");
+  if (!c->keep_ck) return fail(EB_ERR_UNSUPPORTED, "eb_get_ck: the c_k by-product is switched off (eb_set_keep_ck)");
   EB_CUDA(cudaSetDevice(c->cfg.device));
   EB_CUDA(cudaMemcpyAsync(ck, c->d_ck, sizeof(double) * (size_t)c->K * c->B, cudaMemcpyDeviceToHost, c->stream));
   EB_CUDA(cudaStreamSynchronize(c->stream));

@@ -38,6 +38,19 @@ constexpr int kTabSlots = 16;    // time slots per coefficient chunk (half a rou
 constexpr int kTabStride = 20;   // 16 slots + 4 pad: 20 % 16 == 4 -> conflict-free fragment loads
 constexpr int kRecFields = 8;    // per-step record: c_th, s_th, xf, yf, c_a|ex, s_a|ey, c_b, s_b
 
+#ifdef EB_PHASE_TIMING
+// debug build only: per-instance clock64() stamps at the phase boundaries
+constexpr int kPhaseSlots = 8;
+__device__ long long g_phase[65536 * kPhaseSlots];
+#define EB_PHASE(idx)                                                                      \
+  do                                                                                       \
+  {                                                                                        \
+    if (lane == 0 && inst < 65536) g_phase[inst * kPhaseSlots + (idx)] = clock64();        \
+  } while (0)
+#else
+#define EB_PHASE(idx) do { } while (0)
+#endif
+
 struct SolveParams
 {
   int B, N, M, nb;
@@ -208,6 +221,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
 
   const int inst = blockIdx.x * kSolveWarps + warp;
   if (inst >= p.B) return;
+  EB_PHASE(0);
 
   double* tabx = smem + 2 * NB * NB + warp * (2 * NB * kTabStride + kRecFields * npad);
   double* taby = tabx + NB * kTabStride;
@@ -248,16 +262,18 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
     coeff_chunk<NB>(tabx, taby, lane, valid, nvalid, c1x, c1y, acc);
   }
 
+  EB_PHASE(1);
   // ---- forward rollout with the shifted controls (:233-237) ----------------
   const double* ut_in = p.ut_in + (size_t)inst * p.N * 3;
   double* ut_out = p.ut_out + (size_t)inst * p.N * 3;
   RolloutCarry cy;
   {
-    const double* x0 = p.x + (size_t)inst * 3;
-    cy.x = x0[0];
-    cy.y = x0[1];
-    cy.th = x0[2];
-    if (p.pose_out && lane < 3) p.pose_out[(size_t)inst * 3 + lane] = x0[lane];
+    // one 24-byte request per warp (x may live in mapped host memory)
+    const double xv = lane < 3 ? p.x[(size_t)inst * 3 + lane] : 0.0;
+    if (p.pose_out && lane < 3) p.pose_out[(size_t)inst * 3 + lane] = xv;
+    cy.x = __shfl_sync(kFull, xv, 0);
+    cy.y = __shfl_sync(kFull, xv, 1);
+    cy.th = __shfl_sync(kFull, xv, 2);
     fast_sincos(cy.th, &cy.sth, &cy.cth);
   }
   for (int r = 0; r < rounds; r++)
@@ -292,6 +308,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
 
   // ---- c_k, S = lamda .* (c_k - phi_k) (:422), ergodic metric ---------------
   __syncwarp();
+  EB_PHASE(2);
   {
     const int g = lane >> 2, q = lane & 3;
     const double inv_t = 1.0 / (double)(p.M + p.N);  // basis.cpp:119
@@ -308,8 +325,10 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
           if (ky < nb && kx < nb)
           {
             const int k = ky * nb + kx;
-            const double c = inv_t * acc[ti][tj][e];
-            const double d = c - s_phi[k];
+            // explicitly rounded (no FMA contraction): c_k as stored == c_k as used, whichever
+            // way the compiler specialises the p.ck branch
+            const double c = __dmul_rn(inv_t, acc[ti][tj][e]);
+            const double d = __dsub_rn(c, s_phi[k]);
             s = s_lam[k] * d;
             metric += s * d;
             if (p.ck) p.ck[(size_t)inst * K + k] = c;
@@ -321,6 +340,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
   }
   __syncwarp();
 
+  EB_PHASE(3);
   // ---- gradient of the ergodic metric, one time step per lane (:419-436) ----
   for (int r = 0; r < rounds; r++)
   {
@@ -382,6 +402,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
     rec[5 * npad + i] = -ey * p.w;
   }
 
+  EB_PHASE(4);
   // ---- backward co-state pass + control update (:277, :439-451) -------------
   double r0c = 0.0, r1c = 0.0, r2c = 0.0;  // rho(T) = 0 (:203)
   for (int r = rounds - 1; r >= 0; r--)
@@ -451,24 +472,31 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
       bt0 = ce * r0 + se * r1;
       bt1 = 0.0;
     }
-    if (valid)
-    {
-      double un[3];
+    double un[3];
 #pragma unroll
-      for (int c = 0; c < 3; c++)
-      {
-        const double v = -((p.Rinv[c + 0] * bt0 + p.Rinv[c + 3] * bt1) + p.Rinv[c + 6] * r2);
-        un[c] = clampd(v, p.umin[c], p.umax[c]);
-        ut_out[i * 3 + c] = un[c];
-      }
-      if (i == 0)
-      {
-        p.u0[(size_t)inst * 3 + 0] = un[0];
-        p.u0[(size_t)inst * 3 + 1] = un[1];
-        p.u0[(size_t)inst * 3 + 2] = un[2];
-      }
+    for (int c = 0; c < 3; c++)
+    {
+      const double v = -((p.Rinv[c + 0] * bt0 + p.Rinv[c + 3] * bt1) + p.Rinv[c + 6] * r2);
+      un[c] = clampd(v, p.umin[c], p.umax[c]);
+      if (valid) ut_out[i * 3 + c] = un[c];
+    }
+    if (r == 0)
+    {
+      // first twist: lanes 0..2 store one contiguous 24-byte segment (u0 may live in mapped host memory)
+      const double a0 = __shfl_sync(kFull, un[0], 0), a1 = __shfl_sync(kFull, un[1], 0),
+                   a2 = __shfl_sync(kFull, un[2], 0);
+      if (lane < 3) p.u0[(size_t)inst * 3 + lane] = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
     }
   }
+  EB_PHASE(5);
+#ifdef EB_PHASE_TIMING
+  if (lane == 0 && inst < 65536)
+  {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_phase[inst * kPhaseSlots + 6] = smid;
+  }
+#endif
 }
 
 // optTraj() (ergodic_control.hpp:314-317): forward rollout of the CURRENT

@@ -151,6 +151,9 @@ eb_status eb_get_last_mem_idx(const eb_controller *c, int *mem_idx, int *count);
 /* device pointers to the resident state (valid for the handle's lifetime) */
 double *eb_ut_dev(eb_controller *c);
 double *eb_ck_dev(eb_controller *c);
+/* c_k of every instance is a by-product of control() (not part of the reference's
+ * return value); keep = 0 skips its K x B store (default: kept) */
+eb_status eb_set_keep_ck(eb_controller *c, int keep);
 
 /* number of kernels this handle has launched so far */
 long long eb_launch_count(const eb_controller *c);
