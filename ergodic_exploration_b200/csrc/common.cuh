@@ -96,34 +96,74 @@ __device__ __forceinline__ void sincos_kernel(double r, int n, double* s, double
   *c = __hiloint2double(__double2hiint(b) ^ sb, __double2loint(b));
 }
 
-__device__ __noinline__ void slow_sincos(double x, double* s, double* c) { sincos(x, s, c); }
-__device__ __noinline__ void slow_sincospi(double x, double* s, double* c) { sincospi(x, s, c); }
+// Out-of-line library path for arguments beyond 2^30.  Results come back BY
+// VALUE: with pointer outputs the callers' sin / cos variables become
+// address-taken stack objects, and the fused kernel built with nvcc 12.9 then
+// produced wrong fast-path values (reproduced and bisected with
+// tools/diag_dump.py: -DEB_NO_SLOWPATH or this by-value form are both correct).
+__device__ __noinline__ double2 slow_sincos2(double x)
+{
+  double s, c;
+  sincos(x, &s, &c);
+  return make_double2(s, c);
+}
+__device__ __noinline__ double2 slow_sincospi2(double x)
+{
+  double s, c;
+  sincospi(x, &s, &c);
+  return make_double2(s, c);
+}
 
 __device__ __forceinline__ void fast_sincos(double x, double* s, double* c)
 {
+  double sv, cv;
+#ifndef EB_NO_SLOWPATH
   if (fabs(x) > 1073741824.0)
   {
-    slow_sincos(x, s, c);
-    return;
+    const double2 v = slow_sincos2(x);
+    sv = v.x;
+    cv = v.y;
   }
-  const double q = rint(x * kTrigR[0]);
-  double r = fma(-q, kTrigR[1], x);
-  r = fma(-q, kTrigR[2], r);
-  sincos_kernel(r, (int)q, s, c);
+  else
+#endif
+  {
+    const double q = rint(x * kTrigR[0]);
+    double r = fma(-q, kTrigR[1], x);
+    r = fma(-q, kTrigR[2], r);
+    sincos_kernel(r, (int)q, &sv, &cv);
+  }
+  *s = sv;
+  *c = cv;
 }
 
 // sin(pi t), cos(pi t): the reduction t - q/2 is exact
 __device__ __forceinline__ void fast_sincospi(double t, double* s, double* c)
 {
+  double sv, cv;
+#ifndef EB_NO_SLOWPATH
   if (fabs(t) > 1073741824.0)
   {
-    slow_sincospi(t, s, c);
-    return;
+    const double2 v = slow_sincospi2(t);
+    sv = v.x;
+    cv = v.y;
   }
-  const double q = rint(t + t);
-  const double f = fma(-0.5, q, t);  // exact, |f| <= 1/4
-  const double r = fma(f, kTrigR[3], f * kTrigR[4]);
-  sincos_kernel(r, (int)q, s, c);
+  else
+#endif
+  {
+    const double q = rint(t + t);
+    const double f = fma(-0.5, q, t);  // exact, |f| <= 1/4
+    const double r = fma(f, kTrigR[3], f * kTrigR[4]);
+    sincos_kernel(r, (int)q, &sv, &cv);
+  }
+  *s = sv;
+  *c = cv;
+}
+
+__device__ __forceinline__ double fast_cospi(double t)
+{
+  double s, c;
+  fast_sincospi(t, &s, &c);
+  return c;
 }
 
 // numerics.hpp:77-89

@@ -378,8 +378,7 @@ namespace
 template <int MODEL, int NB>
 cudaError_t launch_solve_t(const eb::SolveParams& p, int rounds, cudaStream_t s)
 {
-  const size_t per_warp = sizeof(double) * (2 * NB * eb::kTabStride + eb::kRecFields * 32 * (size_t)rounds);
-  const size_t smem = sizeof(double) * 2 * NB * NB + eb::kSolveWarps * per_warp;
+  const size_t smem = eb::solve_smem_bytes(NB, eb::SolveCfg<NB>::kFields, rounds);
   static size_t configured = 0;  // per instantiation
   if (smem > configured)
   {
@@ -806,6 +805,13 @@ eb_status eb_control_dev(eb_controller* c, double xmin, double xmax, double ymin
 extern "C" int eb_debug_phase_dump(long long* host, int n)
 {
   return (int)cudaMemcpyFromSymbol(host, eb::g_phase, sizeof(long long) * eb::kPhaseSlots * (size_t)n);
+}
+#endif
+
+#ifdef EB_DEBUG_DUMP
+extern "C" int eb_debug_dump(double* host, int n)
+{
+  return (int)cudaMemcpyFromSymbol(host, eb::g_dbg, sizeof(double) * 16 * (size_t)n);
 }
 #endif
 

@@ -24,7 +24,7 @@
 //  * the metric gradient is a pair of bilinear forms per step,
 //    sx^T (a.S) cy and cx^T (S.b) sy: each lane evaluates them for its own time
 //    step with S broadcast from shared memory, cos/sin rows held in registers.
-// Shared memory per warp: 2*NB*20 + 8*32*rounds doubles.
+// Shared memory per warp: 2*NB*20 + (4 or 8)*32*rounds doubles (SolveCfg).
 #pragma once
 
 #include "common.cuh"
@@ -33,10 +33,12 @@ namespace eb
 {
 constexpr int kModelSimpleCart = 0;
 constexpr int kModelOmni = 1;
-constexpr int kSolveWarps = 4;   // warps (instances in flight) per CTA
+#ifndef EB_SOLVE_WARPS
+#define EB_SOLVE_WARPS 4
+#endif
+constexpr int kSolveWarps = EB_SOLVE_WARPS;  // warps (instances in flight) per CTA
 constexpr int kTabSlots = 16;    // time slots per coefficient chunk (half a round)
 constexpr int kTabStride = 20;   // 16 slots + 4 pad: 20 % 16 == 4 -> conflict-free fragment loads
-constexpr int kRecFields = 8;    // per-step record: c_th, s_th, xf, yf, c_a|ex, s_a|ey, c_b, s_b
 
 #ifdef EB_PHASE_TIMING
 // debug build only: per-instance clock64() stamps at the phase boundaries
@@ -49,6 +51,10 @@ __device__ long long g_phase[65536 * kPhaseSlots];
   } while (0)
 #else
 #define EB_PHASE(idx) do { } while (0)
+#endif
+
+#ifdef EB_DEBUG_DUMP
+__device__ double g_dbg[4096 * 16];  // debug build only: per-step intermediates of instance 0
 #endif
 
 struct SolveParams
@@ -134,41 +140,49 @@ __device__ __forceinline__ void rollout_round(const double dt, const bool valid,
 }
 
 // Rank-32 update of the nb x nb coefficient accumulators from one round of
-// (up to) 32 states, in two half-rounds of 16: the lanes of the half write
-// their Chebyshev cosine rows to shared memory (transposed: tab[k][slot]),
-// then the warp runs up to four DMMA k-steps over those 16 states.
+// (up to) 32 states, in two half-rounds of 16 states.  The 32 lanes of the warp
+// build the two cosine tables of a half-round together: lane (axis = lane / 16,
+// slot = lane % 16) runs the Chebyshev recurrence of ONE axis of ONE state and
+// writes its row transposed (tab[k][slot]); the even and odd orders are two
+// independent chains, T_{k+2} = (4c^2 - 2) T_k - T_{k-2}.  Then the warp runs up
+// to four DMMA k-steps over those 16 states.
 template <int NB>
-__device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, double* __restrict__ taby, const int lane,
-                                            const bool valid, const int nvalid, const double c1x,
-                                            const double c1y, double (&acc)[(NB + 7) / 8][(NB + 7) / 8][2])
+__device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, const int lane, const bool valid,
+                                            const int nvalid, const double c1x, const double c1y,
+                                            double (&acc)[(NB + 7) / 8][(NB + 7) / 8][2])
 {
   constexpr int TILES = (NB + 7) / 8;
+  static_assert(NB % 2 == 0, "NB must be even");
   const int g = lane >> 2, q = lane & 3;
+  const double* taby = tabx + NB * kTabStride;
+  double* const mytab = tabx + (lane >> 4) * (NB * kTabStride) + (lane & 15);  // this lane's axis table, its slot
 #pragma unroll
   for (int h = 0; h < 2; h++)
   {
     const int left = nvalid - h * kTabSlots;  // valid states in this half (warp-uniform)
     if (left <= 0) break;
-    __syncwarp();
-    if ((lane >> 4) == h)
     {
-      // T_k(c) by the three-term recurrence, started one step early:
-      // (T_{-1}, T_0) = (c, 1) so that the first advance yields T_1 = c.
-      // Lanes past the end of the trajectory write zero rows (c = 0, T_0 = 0).
-      const int slot = lane & 15;
-      const double vx = valid ? c1x : 0.0, vy = valid ? c1y : 0.0;
-      double xm = vx, xk = valid ? 1.0 : 0.0, ym = vy, yk = xk;
-      const double tx = 2.0 * vx, ty = 2.0 * vy;
+      // state (lane % 16) of this half lives in lane 16 h + lane % 16
+      const int src = 16 * h + (lane & 15);
+      const double sx = __shfl_sync(kFull, c1x, src), sy = __shfl_sync(kFull, c1y, src);
+      const bool ok = __shfl_sync(kFull, (int)valid, src) != 0;
+      const double v = lane < 16 ? sx : sy;
+      // (T_{-2}, T_0) = (2 v^2 - 1, 1), (T_{-1}, T_1) = (v, v); states past the end
+      // of the trajectory give zero rows (the recurrence is homogeneous)
+      const double m = fma(4.0 * v, v, -2.0);
+      double em = ok ? fma(2.0 * v, v, -1.0) : 0.0, ek = ok ? 1.0 : 0.0;
+      double om = ok ? v : 0.0, ok1 = om;
+      __syncwarp();  // the previous half's fragment loads are done
 #pragma unroll
-      for (int k = 0; k < NB; k++)
+      for (int k = 0; k < NB; k += 2)
       {
-        tabx[k * kTabStride + slot] = xk;
-        taby[k * kTabStride + slot] = yk;
-        const double xn = tx * xk - xm, yn = ty * yk - ym;
-        xm = xk;
-        xk = xn;
-        ym = yk;
-        yk = yn;
+        mytab[k * kTabStride] = ek;
+        mytab[(k + 1) * kTabStride] = ok1;
+        const double en = fma(m, ek, -em), on = fma(m, ok1, -om);
+        em = ek;
+        ek = en;
+        om = ok1;
+        ok1 = on;
       }
     }
     __syncwarp();
@@ -192,40 +206,64 @@ __device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, double* _
   }
 }
 
-// resident CTAs per SM the register allocation is tuned for (4 warps per CTA)
+// Per-NB tuning of the fused kernel.
+//  * kRecompute: the per-step record keeps 4 fields (heading cos/sin, Fourier-frame
+//    position) and the gradient pass re-evaluates sincospi of the position, instead
+//    of 8 fields -- ~3 % more FP64 work for 2 KB (N <= 64) less shared memory per
+//    warp, which buys resident warps where shared memory is the limiter.
+//  * kBlock: the gradient's kx range is walked in blocks of kBlock orders so that
+//    only 2 kBlock doubles of cos / sin rows are live in registers.
+//  * kMinBlocks: resident CTAs per SM the register allocation is tuned for.
+#ifndef EB_KB_16
+#define EB_KB_16 8
+#endif
+#ifndef EB_KB_20
+#define EB_KB_20 20
+#endif
+#ifndef EB_MINB_10  // tuning overrides (tools/variants.sh)
+#define EB_MINB_10 7
+#endif
+#ifndef EB_MINB_16
+#define EB_MINB_16 7
+#endif
+#ifndef EB_MINB_20
+#define EB_MINB_20 3
+#endif
 template <int NB>
-constexpr int solve_min_blocks()
+struct SolveCfg
 {
-  return NB <= 10 ? 7 : NB <= 16 ? 5 : NB <= 24 ? 3 : 2;
+  static constexpr bool kRecompute = NB >= 16;
+  static constexpr int kFields = kRecompute ? 4 : 8;
+  static constexpr int kBlock = NB <= 12 ? NB : (NB == 20 ? EB_KB_20 : NB == 16 ? EB_KB_16 : 8);
+  static constexpr int kMinBlocks =
+      (NB <= 10 ? EB_MINB_10 : NB <= 12 ? 6 : NB <= 16 ? EB_MINB_16 : NB <= 24 ? EB_MINB_20 : 4) * 4 / kSolveWarps;
+  static_assert(NB % kBlock == 0, "kx blocks must tile NB");
+};
+
+inline size_t solve_smem_bytes(int NB, int fields, int rounds)
+{
+  return sizeof(double) * kSolveWarps * (size_t)(2 * NB * kTabStride + fields * 32 * rounds);
 }
 
 template <int MODEL, int NB>
-__global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solve_kernel(const SolveParams p)
+__global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) solve_kernel(const SolveParams p)
 {
+  using Cfg = SolveCfg<NB>;
   constexpr int TILES = (NB + 7) / 8;
+  constexpr int KB = Cfg::kBlock;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rounds = (p.N + 31) >> 5;
   const int npad = rounds * 32;
   const int nb = p.nb, K = nb * nb;
 
-  // CTA-shared copies of lamda_k and phi_k (all instances share one target)
-  double* s_lam = smem;
-  double* s_phi = smem + NB * NB;
-  for (int k = threadIdx.x; k < K; k += blockDim.x)
-  {
-    s_lam[k] = p.lamk[k];
-    s_phi[k] = p.phik[k];
-  }
-  __syncthreads();
-
   const int inst = blockIdx.x * kSolveWarps + warp;
   if (inst >= p.B) return;
   EB_PHASE(0);
 
-  double* tabx = smem + 2 * NB * NB + warp * (2 * NB * kTabStride + kRecFields * npad);
-  double* taby = tabx + NB * kTabStride;
-  double* rec = taby + NB * kTabStride;
+  // per-warp shared memory: the two cosine tables, then the per-step records
+  double* tabx = smem + warp * (2 * NB * kTabStride + Cfg::kFields * npad);
+  double* rec = tabx + 2 * NB * kTabStride;
   double* Ssm = tabx;  // S (NB x NB) aliases the two tables (2*NB*20 doubles) once c_k is complete
 
   double acc[TILES][TILES][2];
@@ -254,12 +292,11 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
       if (p.idx_mode != 0 && p.mem_idx_out) p.mem_idx_out[(size_t)inst * p.batch_size + j] = (int)idx;
       const double* h = p.hist + ((size_t)idx * p.B + inst) * 3;
       const double xf = h[0] - p.xmin, yf = h[1] - p.ymin;
-      double sdummy;
-      fast_sincospi(xf * p.inv_lx, &sdummy, &c1x);
-      fast_sincospi(yf * p.inv_ly, &sdummy, &c1y);
+      c1x = fast_cospi(xf * p.inv_lx);
+      c1y = fast_cospi(yf * p.inv_ly);
     }
     const int nvalid = min(32, p.M - base);
-    coeff_chunk<NB>(tabx, taby, lane, valid, nvalid, c1x, c1y, acc);
+    coeff_chunk<NB>(tabx, lane, valid, nvalid, c1x, c1y, acc);
   }
 
   EB_PHASE(1);
@@ -291,19 +328,28 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
     double xo, yo, tho, ce, se;
     rollout_round<MODEL>(p.dt, valid, lane, u0, u1, u2, cy, xo, yo, tho, ce, se);
     const double xf = xo - p.xmin, yf = yo - p.ymin;
-    double ca, sa, cb, sb;
-    fast_sincospi(xf * p.inv_lx, &sa, &ca);
-    fast_sincospi(yf * p.inv_ly, &sb, &cb);
     rec[0 * npad + i] = ce;
     rec[1 * npad + i] = se;
     rec[2 * npad + i] = xf;
     rec[3 * npad + i] = yf;
-    rec[4 * npad + i] = ca;
-    rec[5 * npad + i] = sa;
-    rec[6 * npad + i] = cb;
-    rec[7 * npad + i] = sb;
+    double ca, cb;
+    if (Cfg::kRecompute)
+    {
+      ca = fast_cospi(xf * p.inv_lx);
+      cb = fast_cospi(yf * p.inv_ly);
+    }
+    else
+    {
+      double sa, sb;
+      fast_sincospi(xf * p.inv_lx, &sa, &ca);
+      fast_sincospi(yf * p.inv_ly, &sb, &cb);
+      rec[4 * npad + i] = ca;
+      rec[5 * npad + i] = sa;
+      rec[6 * npad + i] = cb;
+      rec[7 * npad + i] = sb;
+    }
     const int nvalid = min(32, p.N - r * 32);
-    coeff_chunk<NB>(tabx, taby, lane, valid, nvalid, ca, cb, acc);
+    coeff_chunk<NB>(tabx, lane, valid, nvalid, ca, cb, acc);
   }
 
   // ---- c_k, S = lamda .* (c_k - phi_k) (:422), ergodic metric ---------------
@@ -328,96 +374,108 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
             // explicitly rounded (no FMA contraction): c_k as stored == c_k as used, whichever
             // way the compiler specialises the p.ck branch
             const double c = __dmul_rn(inv_t, acc[ti][tj][e]);
-            const double d = __dsub_rn(c, s_phi[k]);
-            s = s_lam[k] * d;
+            const double d = __dsub_rn(c, __ldg(p.phik + k));
+            s = __ldg(p.lamk + k) * d;
             metric += s * d;
             if (p.ck) p.ck[(size_t)inst * K + k] = c;
           }
           if (ky < NB && kx < NB) Ssm[ky * NB + kx] = s;
         }
-    metric = warp_sum(metric);
-    if (p.metric && lane == 0) p.metric[inst] = metric;
+    if (p.metric)
+    {
+      metric = warp_sum(metric);
+      if (lane == 0) p.metric[inst] = metric;
+    }
   }
   __syncwarp();
-
   EB_PHASE(3);
-  // ---- gradient of the ergodic metric, one time step per lane (:419-436) ----
-  for (int r = 0; r < rounds; r++)
-  {
-    const int i = r * 32 + lane;
-    const double ca = rec[4 * npad + i], sa = rec[5 * npad + i];
-    const double cb = rec[6 * npad + i], sb = rec[7 * npad + i];
-    double cx[NB], asx[NB];  // cos(kx a x), a_kx sin(kx a x)
-    {
-      // (cos, sin)((k-1) t), (cos, sin)(k t) started at k = 0
-      double cm = ca, ck = 1.0, sm = -sa, sk = 0.0;
-      const double t2 = 2.0 * ca;
-#pragma unroll
-      for (int k = 0; k < NB; k++)
-      {
-        cx[k] = ck;
-        asx[k] = ((double)k * p.ax) * sk;
-        const double cn = t2 * ck - cm, sn = t2 * sk - sm;
-        cm = ck;
-        ck = cn;
-        sm = sk;
-        sk = sn;
-      }
-    }
-    double ex = 0.0, ey = 0.0;
-    {
-      double cm = cb, ck = 1.0, sm = -sb, sk = 0.0;  // cos/sin(ky b y), advanced in the loop
-      const double t2 = 2.0 * cb;
-#pragma unroll 2
-      for (int ky = 0; ky < NB; ky++)
-      {
-        double rx0 = 0.0, rx1 = 0.0, ry0 = 0.0, ry1 = 0.0;
-        const double* srow = Ssm + ky * NB;
-#pragma unroll
-        for (int kx = 0; kx + 1 < NB; kx += 2)
-        {
-          const double2 s2 = *reinterpret_cast<const double2*>(srow + kx);
-          rx0 = fma(s2.x, asx[kx], rx0);
-          rx1 = fma(s2.y, asx[kx + 1], rx1);
-          ry0 = fma(s2.x, cx[kx], ry0);
-          ry1 = fma(s2.y, cx[kx + 1], ry1);
-        }
-        if (NB & 1)
-        {
-          const double s1 = srow[NB - 1];
-          rx0 = fma(s1, asx[NB - 1], rx0);
-          ry0 = fma(s1, cx[NB - 1], ry0);
-        }
-        ex = fma(ck, rx0 + rx1, ex);
-        ey = fma(((double)ky * p.by) * sk, ry0 + ry1, ey);
-        const double cn = t2 * ck - cm, sn = t2 * sk - sm;
-        cm = ck;
-        ck = cn;
-        sm = sk;
-        sk = sn;
-      }
-    }
-    // dF/dx = -a sin(a x) cos(b y), dF/dy = -b cos(a x) sin(b y); times expl_weight (:433)
-    rec[4 * npad + i] = -ex * p.w;
-    rec[5 * npad + i] = -ey * p.w;
-  }
 
-  EB_PHASE(4);
-  // ---- backward co-state pass + control update (:277, :439-451) -------------
+  // ---- per round, last round first: gradient of the ergodic metric, one time
+  //      step per lane (:419-436), then the backward co-state pass and the
+  //      control update of the same 32 steps (:277, :439-451) -------------------
   double r0c = 0.0, r1c = 0.0, r2c = 0.0;  // rho(T) = 0 (:203)
   for (int r = rounds - 1; r >= 0; r--)
   {
     const int i = r * 32 + lane;
     const bool valid = i < p.N;
+    const double ce = rec[0 * npad + i], se = rec[1 * npad + i];
+    const double xf = rec[2 * npad + i], yf = rec[3 * npad + i];
+    double ca, sa, cb, sb;
+    if (Cfg::kRecompute)
+    {
+      fast_sincospi(xf * p.inv_lx, &sa, &ca);
+      fast_sincospi(yf * p.inv_ly, &sb, &cb);
+    }
+    else
+    {
+      ca = rec[4 * npad + i];
+      sa = rec[5 * npad + i];
+      cb = rec[6 * npad + i];
+      sb = rec[7 * npad + i];
+    }
+    double ex = 0.0, ey = 0.0;
+    {
+      // (cos, sin)((k-1) a x), (cos, sin)(k a x) started at k = 0, carried across the kx blocks
+      double xcm = ca, xck = 1.0, xsm = -sa, xsk = 0.0;
+      const double xt2 = 2.0 * ca, yt2 = 2.0 * cb;
+#pragma unroll
+      for (int kb = 0; kb < NB; kb += KB)
+      {
+        double cx[KB], asx[KB];  // cos(kx a x), a_kx sin(kx a x) for kx = kb .. kb + KB - 1
+#pragma unroll
+        for (int j = 0; j < KB; j++)
+        {
+          cx[j] = xck;
+          asx[j] = ((double)(kb + j) * p.ax) * xsk;
+          const double cn = xt2 * xck - xcm, sn = xt2 * xsk - xsm;
+          xcm = xck;
+          xck = cn;
+          xsm = xsk;
+          xsk = sn;
+        }
+        double cm = cb, ck = 1.0, sm = -sb, sk = 0.0;  // cos/sin(ky b y), advanced in the loop
+#pragma unroll 2
+        for (int ky = 0; ky < NB; ky++)
+        {
+          double rx0 = 0.0, rx1 = 0.0, ry0 = 0.0, ry1 = 0.0;
+          const double* srow = Ssm + ky * NB + kb;
+#pragma unroll
+          for (int j = 0; j < KB; j += 2)
+          {
+            const double2 s2 = *reinterpret_cast<const double2*>(srow + j);
+            rx0 = fma(s2.x, asx[j], rx0);
+            rx1 = fma(s2.y, asx[j + 1], rx1);
+            ry0 = fma(s2.x, cx[j], ry0);
+            ry1 = fma(s2.y, cx[j + 1], ry1);
+          }
+          ex = fma(ck, rx0 + rx1, ex);
+          ey = fma(((double)ky * p.by) * sk, ry0 + ry1, ey);
+          const double cn = yt2 * ck - cm, sn = yt2 * sk - sm;
+          cm = ck;
+          ck = cn;
+          sm = sk;
+          sk = sn;
+        }
+      }
+    }
+    // dF/dx = -a sin(a x) cos(b y), dF/dy = -b cos(a x) sin(b y); times expl_weight (:433)
+    ex = -ex * p.w;
+    ey = -ey * p.w;
+#ifdef EB_DEBUG_DUMP
+    if (inst == 0 && i < 4096)
+    {
+      double* d = g_dbg + i * 16;
+      d[0] = ex; d[1] = ey; d[2] = ca; d[3] = sa; d[4] = cb; d[5] = sb; d[6] = ce; d[7] = se; d[8] = xf; d[9] = yf;
+      d[10] = Ssm[lane % (NB * NB)];
+    }
+#endif
+
     double u0 = 0.0, u1 = 0.0;
     if (i + 1 < p.N)
     {
       u0 = ut_in[(i + 1) * 3 + 0];
       u1 = ut_in[(i + 1) * 3 + 1];
     }
-    const double ce = rec[0 * npad + i], se = rec[1 * npad + i];
-    const double xf = rec[2 * npad + i], yf = rec[3 * npad + i];
-    const double ex = rec[4 * npad + i], ey = rec[5 * npad + i];
     // gradBarrier :454-474
     double bx = 0.0, byv = 0.0;
     bx += 2.0 * (double)(xf > p.lx - p.beps) * (xf - (p.lx - p.beps));
@@ -488,7 +546,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, solve_min_blocks<NB>()) solv
       if (lane < 3) p.u0[(size_t)inst * 3 + lane] = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
     }
   }
-  EB_PHASE(5);
+  EB_PHASE(4);
 #ifdef EB_PHASE_TIMING
   if (lane == 0 && inst < 65536)
   {

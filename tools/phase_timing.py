@@ -45,16 +45,16 @@ torch.cuda.synchronize()
 lib = capi.load()
 buf = np.zeros((B, 8), dtype=np.int64)
 assert lib.eb_debug_phase_dump(buf.ctypes.data_as(C.c_void_p), B) == 0
-names = ["replay c_k", "rollout + c_k", "S / metric", "gradient", "co-state + update"]
+names = ["replay c_k", "rollout + c_k", "S / metric", "gradient + co-state"]
 sm = buf[:, 6]
 print(f"workload {name}: {B} instances; stamps are per-SM clocks, spans are per SM then averaged")
 spans = []
 for s in np.unique(sm):
     t = buf[sm == s]
-    spans.append((t[:, 5].max() - t[:, 0].min(), len(t)))
+    spans.append((t[:, 4].max() - t[:, 0].min(), len(t)))
 spans = np.array(spans)
 print(f"SM busy span: mean {spans[:, 0].mean():.0f} cycles, max {spans[:, 0].max():.0f}; warps per SM {spans[:, 1].mean():.1f}")
-tot = (buf[:, 5] - buf[:, 0]).mean()
+tot = (buf[:, 4] - buf[:, 0]).mean()
 for i, n in enumerate(names):
     d = buf[:, i + 1] - buf[:, i]
     print(f"  {n:20s} mean {d.mean():9.0f} cycles  ({100 * d.mean() / tot:5.1f}% of a warp's {tot:.0f})  min {d.min()} max {d.max()}")
