@@ -412,61 +412,131 @@ def run_ours(args, wl, rank, world, local_rank):
 
 
 def run_phik(args, rank, world, local_rank):
-    """secondary metric: phi_k grid cells*bases/sec (configs[2]: 8192^2 grid, 32x32 basis)"""
+    """secondary metric: phi_k grid cells*bases/sec (configs[2]: 8192^2 grid, 32x32 basis).
+    N > 1: the grid is row-sharded (strong scaling of the one contraction), every rank
+    contracts its row block and one all_reduce of the raw 32x32 block finishes it."""
     import torch
+    import torch.distributed as dist
 
     import ergodic_exploration_b200 as eb
+    from ergodic_exploration_b200.sharding import finish_phik, shard_bounds
 
-    if rank != 0:
-        return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     nx = ny = 8192
     nb, res = 32, 0.1
     lx = ly = (nx - 1) * res
+    lo, hi = shard_bounds(ny, world, rank)
     g = torch.Generator(device=dev).manual_seed(0xE16C0D1C + 3)
     xs = torch.arange(nx, device=dev, dtype=torch.float64) * res
-    phi = torch.zeros((ny, nx), dtype=torch.float64, device=dev)
-    for _ in range(8):  # un-normalised mixture of 8 Gaussians (SURVEY §8d C3)
+    ys = torch.arange(lo, hi, device=dev, dtype=torch.float64) * res
+    phi = torch.zeros((hi - lo, nx), dtype=torch.float64, device=dev)
+    for _ in range(8):  # un-normalised mixture of 8 Gaussians (SURVEY §8d C3); same stream on every rank
         mu = (0.1 + 0.8 * torch.rand(2, generator=g, device=dev, dtype=torch.float64)) * lx
         sg = (0.02 + 0.08 * torch.rand(2, generator=g, device=dev, dtype=torch.float64)) * lx
-        phi += torch.exp(-0.5 * ((xs[None, :] - mu[0]) / sg[0]) ** 2 - 0.5 * ((xs[:, None] - mu[1]) / sg[1]) ** 2)
-    plan = eb.PhikPlan(nx, ny, res, lx, ly, nb, device=local_rank)
+        phi += torch.exp(-0.5 * ((xs[None, :] - mu[0]) / sg[0]) ** 2 - 0.5 * ((ys[:, None] - mu[1]) / sg[1]) ** 2)
+    algo = int(os.environ.get("EB_PHIK_ALGO", "0"))
+    plan = eb.PhikPlan(nx, hi - lo, res, lx, ly, nb, device=local_rank, algo=algo, row_begin=lo, ny_total=ny)
+    fold, fold_dev = plan.fold()
+    fold = fold and algo != 3
+    raw = torch.empty((32, 32), dtype=torch.float64, device=dev)
     out = torch.empty(nb * nb, dtype=torch.float64, device=dev)
+
+    def step():
+        if world > 1:
+            plan.execute_raw(phi, raw)
+            return finish_phik(raw, nb)[0]
+        return plan.execute(phi, out)
+
     for _ in range(max(3, args.warmup)):
-        plan.execute(phi, out)
+        step()
     torch.cuda.synchronize()
     clocks = ClockSampler(local_rank)
-    clocks.start()
+    if rank == 0:
+        clocks.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     l0 = plan.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda._sleep(int(min(args.steps, 400) * 100e-6 * 1.9e9))  # host enqueues ahead of the device
     for a, b in ev:
         a.record()
-        plan.execute(phi, out)
+        step()
         b.record()
     torch.cuda.synchronize()
-    clk = clocks.stop()
+    if world > 1:
+        dist.barrier()
+    launches = plan.launch_count() - l0
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+
+    # end to end (N = 1): pageable/pinned host density in, phi_k out, through eb_phik_execute_host
+    e2e = None
+    if world == 1:
+        phih = phi.cpu().pin_memory()
+        phin = phih.numpy()
+        plan.execute(phin)
+        t0 = time.perf_counter()
+        reps = max(2, min(args.steps, 5))
+        for _ in range(reps):
+            plan.execute(phin)
+        e2e_s = (time.perf_counter() - t0) / reps
+        e2e = {"value": nx * ny * nb * nb / e2e_s, "unit": "cell*bases/s", "h2d_bytes_per_step": 8 * nx * ny,
+               "d2h_bytes_per_step": 8 * nb * nb + 8, "ms_per_step": e2e_s * 1e3,
+               "path": "eb_phik_execute_host: pinned host density -> H2D (512 MiB, PCIe-bound) -> tile kernel -> D2H phi_k"}
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     dfma, dmma = eb.fp64_peak(local_rank)
-    flops = 2.0 * nx * ny * nb + 2.0 * ny * nb * nb
+    peak64 = max(dfma, dmma)
+    flops = 2.0 * nx * ny * nb + 2.0 * ny * nb * nb  # SURVEY §8(d) algorithmic count (unfolded)
+    done_flops = flops / 2 if fold else flops       # the fold halves the DMMA work actually issued
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_traffic.json"))).get("c3")
+    except Exception:
+        pass
+    sec = ms * 1e-3 * world  # per-GPU seconds of kernel work behind one step (row shards run concurrently)
+    hbm = {"achieved": 8.0 * nx * ny / world / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+           "frac": 8.0 * nx * ny / world / (ms * 1e-3) / 1e9 / hbm_peak,
+           "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
+    f64 = {"achieved": done_flops / world / (ms * 1e-3) / 1e12, "peak": peak64, "unit": "TFLOP/s",
+           "frac": done_flops / world / (ms * 1e-3) / 1e12 / peak64,
+           "flops_issued_over_algorithmic": 0.5 if fold else 1.0,
+           "peak_source": f"measured live by eb_fp64_peak (DFMA {dfma:.2f}, DMMA {dmma:.2f} TFLOP/s)"}
+    del sec
+    bound = "hbm" if fold else "fp64"
+    main_ = hbm if fold else f64
     line = {
         "metric": "phi_k grid cells*bases/sec", "value": nx * ny * nb * nb / (ms * 1e-3), "unit": "cell*bases/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
         "config": {"workload": "configs[2]: phi_k over 8192x8192 Gaussian-mixture grid, 32x32 basis",
-                   "l2": "input (512 MiB) larger than L2"},
-        "gpu_launches": int(plan.launch_count() - l0), "clocks": clk,
-        "roofline": {"kernel": "phik contraction", "bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12,
-                     "peak": max(dfma, dmma), "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / max(dfma, dmma),
-                     "traffic": None,
-                     "hbm": {"achieved": 8.0 * nx * ny / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}},
+                   "l2": "input (512 MiB per step) larger than L2", "mirror_fold": bool(fold),
+                   "table_asymmetry": fold_dev,
+                   "parallelism": f"rows sharded over {world} GPUs, one all_reduce of the raw 32x32 block" if world > 1
+                   else "single GPU"},
+        "gpu_launches": int(launches), "clocks": clk,
+        "roofline": {"kernel": "phik_dmma_kernel", "bound": bound, "achieved": main_["achieved"], "peak": main_["peak"],
+                     "unit": main_["unit"], "frac": main_["frac"], "traffic": traffic, "kernel_ms": ms,
+                     "hbm": hbm, "fp64": f64},
     }
+    if e2e:
+        line["e2e"] = e2e
     print(json.dumps(line), flush=True)
 
 

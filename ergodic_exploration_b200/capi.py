@@ -98,6 +98,7 @@ SIGNATURES = {
     "eb_phik_plan_destroy": (None, [_vp]),
     "eb_phik_plan_set_stream": (C.c_int, [_vp, _vp]),
     "eb_phik_plan_set_algo": (C.c_int, [_vp, C.c_int]),
+    "eb_phik_plan_fold": (C.c_int, [_vp, _ip, _dp]),
     "eb_phik_execute_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "eb_phik_execute_host": (C.c_int, [_vp, _vp, _vp, _vp]),
     "eb_phik_execute_raw_dev": (C.c_int, [_vp, _vp, _vp]),

@@ -324,6 +324,12 @@ class PhikPlan:
     def launch_count(self) -> int:
         return int(self._lib.eb_phik_launch_count(self._h))
 
+    def fold(self):
+        """(mirror fold usable on this grid, measured asymmetry of the cosine table)"""
+        f, d = C.c_int(0), C.c_double(0.0)
+        check(self._lib.eb_phik_plan_fold(self._h, C.byref(f), C.byref(d)))
+        return bool(f.value), d.value
+
 
 def fp64_peak(device: int = 0):
     """Measured FP64 TFLOP/s of the device: (DFMA loop, DMMA loop)."""

@@ -73,6 +73,10 @@ std::vector<double> accumulated_axis(int n, double resolution)
 // ---------------------------------------------------------------------------
 // phi_k plan
 // ---------------------------------------------------------------------------
+// The mirror fold of the tile kernel (phik_dmma.cuh) is taken when the cosine table of
+// the plan's grid is symmetric to this tolerance; it bounds the fold's coefficient error.
+constexpr double kFoldTol = 1.0e-10;
+
 struct eb_phik_plan
 {
   int device = 0, nx = 0, ny = 0, nb = 0, algo = 0;  // ny = rows held by this plan
@@ -82,6 +86,9 @@ struct eb_phik_plan
   double *d_xs = nullptr, *d_ys = nullptr;  // grid coordinates
   double *d_cx = nullptr, *d_cy = nullptr;  // cosine tables [n][32]
   double* d_cxp = nullptr;                  // C_x re-laid for the DMMA tile kernel
+  double* d_cxpf = nullptr;                 // ... for the mirror-folded tile kernel (left half, even | odd orders)
+  bool fold = false;                        // the grid's cosine tables are mirror-symmetric to <= kFoldTol
+  double fold_dev = 0.0;                    // measured max |C_x[j][k] - (-1)^k C_x[nx-1-j][k]|
   double *d_T = nullptr;                    // stage-1 result [ny][32]
   double *d_parts = nullptr;                // partial 32x32 blocks
   double *d_phik = nullptr, *d_sum = nullptr;  // staging for the _host call
@@ -199,8 +206,30 @@ eb_status eb_phik_plan_create_rows(int device, int nx, int ny_total, int row_beg
     // room for the last column span's padding chunks (span <= nchunks)
     const int rows_padded = 2 * ((nx + eb::kPdChunk - 1) / eb::kPdChunk) * eb::kPdChunk;
     EB_CUDA_P(cudaMalloc(&p->d_cxp, sizeof(double) * (size_t)rows_padded * eb::kPdPitch));
-    eb::phik_permute_cx<<<(rows_padded * eb::kPdPitch + 255) / 256, 256>>>(p->d_cx, nx, rows_padded, p->d_cxp);
+    eb::phik_permute_cx<<<(rows_padded * eb::kPdPitch + 255) / 256, 256>>>(p->d_cx, nx, rows_padded, 0, p->d_cxp);
     p->launches += 1;
+    if (eb::phik_fold_shape_ok(nx))
+    {
+      // symmetry of the table on THIS grid (accumulated coordinates, caller's lx), basis.cpp:85 arithmetic
+      double dev = 0.0;
+      for (int j = 0; j < nx / 2; j++)
+        for (int k = 0; k < nb; k++)
+        {
+          const double f = (double)k * (eb::kPi / lx);
+          const double a = std::cos(f * xs[j]), b = std::cos(f * xs[nx - 1 - j]);
+          dev = std::max(dev, std::fabs(a - ((k & 1) ? -b : b)));
+        }
+      p->fold_dev = dev;
+      p->fold = dev <= kFoldTol;
+      if (p->fold)
+      {
+        const int chunk = eb::PdGeom<true>::kChunk;
+        const int rows_f = 2 * ((nx / 2 + chunk - 1) / chunk) * chunk;
+        EB_CUDA_P(cudaMalloc(&p->d_cxpf, sizeof(double) * (size_t)rows_f * eb::kPdPitch));
+        eb::phik_permute_cx<<<(rows_f * eb::kPdPitch + 255) / 256, 256>>>(p->d_cx, nx / 2, rows_f, 1, p->d_cxpf);
+        p->launches += 1;
+      }
+    }
   }
   EB_CUDA_P(cudaGetLastError());
   EB_CUDA_P(cudaDeviceSynchronize());
@@ -218,6 +247,7 @@ void eb_phik_plan_destroy(eb_phik_plan* p)
   cudaFree(p->d_cx);
   cudaFree(p->d_cy);
   cudaFree(p->d_cxp);
+  cudaFree(p->d_cxpf);
   cudaFree(p->d_T);
   cudaFree(p->d_parts);
   cudaFree(p->d_phik);
@@ -235,14 +265,23 @@ eb_status eb_phik_plan_set_stream(eb_phik_plan* p, void* s)
 eb_status eb_phik_plan_set_algo(eb_phik_plan* p, int algo)
 {
   if (!p) return fail(EB_ERR_INVALID_ARGUMENT, "plan is NULL");
-  if (algo < 0 || algo > 2) return fail(EB_ERR_INVALID_ARGUMENT, "algo must be 0 (auto), 1 (simple) or 2 (dmma)");
-  if (algo == 2 && !eb::phik_dmma_supported(p->nx, p->ny))
+  if (algo < 0 || algo > 3)
+    return fail(EB_ERR_INVALID_ARGUMENT, "algo must be 0 (auto), 1 (simple), 2 (dmma tiles) or 3 (dmma tiles, no mirror fold)");
+  if (algo >= 2 && !eb::phik_dmma_supported(p->nx, p->ny))
     return fail(EB_ERR_UNSUPPORTED, "the DMMA phi_k kernel needs nx % 4 == 0 and nx >= 128");
   p->algo = algo;
   return EB_OK;
 }
 
 long long eb_phik_launch_count(const eb_phik_plan* p) { return p ? p->launches : 0; }
+
+eb_status eb_phik_plan_fold(const eb_phik_plan* p, int* fold, double* deviation)
+{
+  if (!p) return fail(EB_ERR_INVALID_ARGUMENT, "plan is NULL");
+  if (fold) *fold = p->fold ? 1 : 0;
+  if (deviation) *deviation = p->fold_dev;
+  return EB_OK;
+}
 
 static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* phik_dev, double* phi_sum_dev,
                               double* raw_dev);
@@ -266,9 +305,11 @@ static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* ph
   int algo = p->algo;
   if (algo == 0) algo = (eb::phik_dmma_supported(p->nx, p->ny) && (long long)p->nx * p->ny >= (1 << 18)) ? 2 : 1;
   int nparts = 1;
-  if (algo == 2)
+  const bool fold = algo == 2 && p->fold;
+  if (algo >= 2)
   {
-    nparts = eb::phik_dmma_launch(phi_dev, p->nx, p->ny, p->d_cxp, p->d_cy, p->d_parts, p->max_parts, p->stream);
+    nparts = eb::phik_dmma_launch(phi_dev, p->nx, p->ny, fold ? p->d_cxpf : p->d_cxp, p->d_cy, p->d_parts, p->max_parts,
+                                  fold, p->stream);
     if (nparts < 0) return fail(EB_ERR_CUDA, std::string("phik_dmma_launch: ") + cudaGetErrorString(cudaGetLastError()));
     p->launches += 1;
   }
@@ -278,7 +319,7 @@ static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* ph
     eb::phik_stage2_simple<<<32, 256, 0, p->stream>>>(p->d_T, p->ny, p->d_cy, p->d_parts);
     p->launches += 2;
   }
-  eb::phik_finalize<<<1, 1024, 0, p->stream>>>(p->d_parts, nparts, p->nb, phik_dev, phi_sum_dev, raw_dev);
+  eb::phik_finalize<<<1, 1024, 0, p->stream>>>(p->d_parts, nparts, p->nb, fold ? 1 : 0, phik_dev, phi_sum_dev, raw_dev);
   p->launches += 1;
   EB_CUDA(cudaGetLastError());
   return EB_OK;

@@ -4,10 +4,11 @@
 // dense densities (config C3: 8192 x 8192 grid, 32 x 32 basis).  Algorithmic
 // work: 8*nx*ny bytes (Phi read once) and 2*nx*ny*nb + 2*ny*nb^2 flops.
 //
-// Decomposition.  A work unit is 64 rows x (span * 128) columns of Phi.  A
-// persistent CTA (16 consumer warps + 1 producer warp, one CTA per SM) walks its
-// units; inside a unit consumer warp w owns rows 8*(w%8)..+8 and the (w/8)-th
-// 64-column half of every chunk:
+// Decomposition.  The grid is cut into 64-row bands and every band into chunks of
+// 128 columns; the (band, chunk) iterations are numbered band-major and each
+// persistent CTA (16 consumer warps + 1 producer warp, one CTA per SM) takes a
+// contiguous range of them.  Consumer warp w owns rows 8*(w%8)..+8 of the band and
+// the (w/8)-th 64-column half of every chunk:
 //     T[8 rows][32 kx] += Phi[8 rows][4 cols] * C_x[4 cols][32 kx]      (DMMA m8n8k4 x 4)
 //  * Phi is streamed straight from HBM into the A fragments: each lane keeps a
 //    register double buffer of four 32-byte loads per chunk (64 KB in flight
@@ -18,15 +19,31 @@
 //    (cp.async.bulk -> UBLKCP) into a three-stage ring with full/empty
 //    mbarriers, issued by a dedicated producer warp, so the consumer warps never
 //    meet at a CTA barrier inside a unit; the chunk rows are stored pre-permuted
-//    so the B-fragment loads are bank-conflict free.  The producer warp also
-//    runs cp.async.bulk.prefetch.L2 over the Phi rows two chunk iterations
-//    ahead, so the register window is refilled at L2 latency, not HBM latency.
-//  * at the end of a unit the two column halves' tiles are summed in a
+//    so the B-fragment loads are bank-conflict free.  (The producer warp can
+//    also run cp.async.bulk.prefetch.L2 over the band in front of the consumers;
+//    with the band-major streaming order it only competes with the demand loads
+//    -- measured 0.13 ms without vs 0.18-0.21 ms with, 8192^2 folded -- so the
+//    window defaults to 0 and stays as a tuning knob, EB_PHIK_AHEAD / _PFLEN.)
+//  * at the end of a band (or of the CTA's range) the two column halves' tiles are summed in a
 //    64 x 32 shared-memory stage and the CTA folds it into its running 32 x 32
 //    partial with C_y:  P[ky][kx] += C_y[64 rows][ky]^T * T, one 8 x 8 output
-//    tile per warp (16 DMMAs each, ~3 % extra work at span = 8).
+//    tile per warp (16 DMMAs each; once or twice per CTA on a large grid).
 // Every CTA writes one 32 x 32 partial; phik_finalize sums them in a fixed
 // order (deterministic) and normalises by P[0][0] = sum(Phi).
+//
+// Mirror fold (FOLD = true).  On the configTarget grid x_j = j * res with
+// lx = (nx - 1) * res, so cos(k pi x_{nx-1-j} / lx) = (-1)^k cos(k pi x_j / lx):
+// the even orders see only Phi[j] + Phi[nx-1-j] and the odd orders only
+// Phi[j] - Phi[nx-1-j].  A lane loads 32 bytes from the left half of the row and
+// the mirrored 32 bytes from the right half, forms the sum and the difference
+// (2 DADD per column pair) and runs HALF the DMMAs: sum x 16 even orders,
+// difference x 16 odd orders.  This exploits a symmetry of the BASIS on this
+// grid, not any structure of the density.  The plan takes the fold only when the
+// measured table symmetry max|C_x[j][k] - (-1)^k C_x[nx-1-j][k]| (accumulated
+// grid coordinates are not exactly symmetric) is <= 1e-10, which bounds the
+// coefficient error by the same number -- 10x inside the 1e-9 contract; other
+// grids (odd nx, lx != (nx-1) res) use FOLD = false.  With the fold the kernel
+// is HBM-bound at nb = 32 (4 flop/B against a ridge of ~5.7).
 #pragma once
 
 #include <cstdlib>
@@ -36,29 +53,32 @@
 namespace eb
 {
 constexpr int kPdRows = 64;         // rows per unit (8 row groups of 8)
-constexpr int kPdChunk = 128;       // columns per C_x chunk
+constexpr int kPdChunk = 128;       // columns per C_x chunk (64 column pairs with the mirror fold, PdGeom)
 constexpr int kPdPitch = 36;        // doubles per chunk row: 36*8 B = 288 = 32 (mod 128) -> conflict-free
 constexpr int kPdWarps = 16;        // consumer warps: 8 row groups x 2 column halves of every chunk
 constexpr int kPdThreads = (kPdWarps + 1) * 32;  // + 1 producer warp (TMA issue, L2 prefetch of Phi)
 constexpr int kPdStages = 3;        // C_x ring depth
-constexpr int kPdAhead = 2;         // Phi is prefetched into L2 this many chunk iterations ahead
-constexpr int kPdChunkBytes = kPdChunk * kPdPitch * 8;  // 36864
+constexpr int kPdAhead = 0;         // L2 prefetch window in front of the consumers, in chunks (0: off)
+constexpr int kPdPfLen = 8;         // ... extended in pieces of this many chunks per row
 constexpr int kPdStagePitch = 33;
-constexpr int kPdSmemBytes = kPdStages * kPdChunkBytes + kPdRows * kPdStagePitch * 8 + 128;
 
 inline bool phik_dmma_supported(int nx, int ny) { return nx % 4 == 0 && nx >= kPdChunk && ny >= 1; }
 
-// C_x table re-laid for the tile kernel: rows padded to a multiple of 128,
+// C_x table re-laid for the tile kernel: rows padded to a multiple of the chunk,
 // pitch 36, and within every group of 16 columns column (4q + s) is stored at
 // row (4s + q) so that lanes (q, g) of a B-fragment load hit distinct banks.
-__global__ void phik_permute_cx(const double* __restrict__ cx, int nx, int rows_padded, double* __restrict__ out)
+// fold: only the left nx/2 columns, and the 32 orders re-ordered as
+// [0, 2, .., 30 | 1, 3, .., 31] (even orders multiply the mirror sum, odd the difference).
+__global__ void phik_permute_cx(const double* __restrict__ cx, int ncols, int rows_padded, int fold,
+                                double* __restrict__ out)
 {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows_padded * kPdPitch) return;
   const int j = idx / kPdPitch, k = idx % kPdPitch;
   const int G = j >> 4, w = j & 15, q = w >> 2, s = w & 3;
   const int row = 16 * G + 4 * s + q;
-  out[(size_t)row * kPdPitch + k] = (j < nx && k < 32) ? cx[(size_t)j * 32 + k] : 0.0;
+  const int order = fold ? (k < 16 ? 2 * k : 2 * (k - 16) + 1) : k;
+  out[(size_t)row * kPdPitch + k] = (j < ncols && k < 32) ? cx[(size_t)j * 32 + order] : 0.0;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,42 +145,62 @@ __device__ __forceinline__ void ldg_stream4(const double* p, bool pred, double (
 struct PhikDmmaParams
 {
   const double* phi;   // [ny][nx]
-  const double* cxp;   // permuted C_x, [nchunks*128][36]
+  const double* cxp;   // permuted C_x, [nchunks*CH][36]
   const double* cy;    // C_y, [ny][32]
   double* parts;       // [gridDim.x][1024]
-  int nx, ny, nchunks, span, nspans, nunits, ahead;
+  int nx, ny;          // grid
+  int ncols;           // logical columns walked by the chunks: nx, or nx / 2 with the mirror fold
+  int nchunks;         // chunk iterations per row block
+  long long total;     // row_blocks * nchunks chunk iterations, row-block-major
+  int ahead, pflen;    // L2 prefetch window / piece, in chunks (0: off)
 };
 
-// iteration cursor: unit id + chunk index inside the unit, advanced without divisions
+// Work distribution.  The (row block, chunk) iterations are numbered row-block-major
+// and CTA b takes the contiguous range [b * total / grid, (b + 1) * total / grid): every
+// SM streams whole 64-row bands left to right (long sequential runs per DRAM row, one
+// C_y fold per band) and the load is balanced to one iteration whatever the grid shape.
+// A band shared by two CTAs is simply folded with C_y by both -- the fold is linear.
 struct PdCursor
 {
-  int unit, k, rb, cs;
-  __device__ __forceinline__ void init(const PhikDmmaParams& p, int first_unit)
+  int rb, k;
+  __device__ __forceinline__ void init(const PhikDmmaParams& p, long long it)
   {
-    unit = first_unit;
-    k = 0;
-    rb = unit / p.nspans;
-    cs = unit - rb * p.nspans;
+    rb = (int)(it / p.nchunks);
+    k = (int)(it - (long long)rb * p.nchunks);
   }
-  __device__ __forceinline__ void advance(const PhikDmmaParams& p, int stride)
+  __device__ __forceinline__ void advance(const PhikDmmaParams& p)
   {
-    if (++k == p.span)
+    if (++k == p.nchunks)
     {
       k = 0;
-      unit += stride;
-      rb = unit / p.nspans;
-      cs = unit - rb * p.nspans;
+      rb++;
     }
   }
-  __device__ __forceinline__ int chunk(const PhikDmmaParams& p) const { return cs * p.span + k; }
 };
 
+// Geometry of one chunk iteration.  Unfolded: 128 columns, a consumer warp owns 64
+// of them (4 groups of 16).  Folded: 64 column PAIRS (64 left columns + their 64
+// mirror columns), a consumer warp owns 32 pairs (2 groups) -- the same 16 doubles
+// of Phi per lane and chunk, so the register double buffer is unchanged.
+template <bool FOLD>
+struct PdGeom
+{
+  static constexpr int kChunk = FOLD ? 64 : 128;
+  static constexpr int kGroups = kChunk / 32;             // 16-column groups per warp and chunk
+  static constexpr int kChunkBytes = kChunk * kPdPitch * 8;  // C_x stage
+  static constexpr int kSmemBytes = kPdStages * kChunkBytes + kPdRows * kPdStagePitch * 8 + 128;
+};
+
+template <bool FOLD>
 __global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmmaParams p)
 {
+  using G = PdGeom<FOLD>;
+  constexpr int CH = G::kChunk, GR = G::kGroups, NV = FOLD ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* const cxs0 = reinterpret_cast<double*>(smem_raw);
-  double* const tstage = reinterpret_cast<double*>(smem_raw + kPdStages * kPdChunkBytes);  // [64][33]
-  uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + kPdStages * kPdChunkBytes + kPdRows * kPdStagePitch * 8);
+  double* const tstage = reinterpret_cast<double*>(smem_raw + kPdStages * G::kChunkBytes);  // [64][33]
+  uint64_t* const full =
+      reinterpret_cast<uint64_t*>(smem_raw + kPdStages * G::kChunkBytes + kPdRows * kPdStagePitch * 8);
   uint64_t* const empty = full + kPdStages;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -176,45 +216,56 @@ __global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmma
   }
   __syncthreads();
 
-  // this CTA's units are blockIdx.x, blockIdx.x + gridDim.x, ...; each is `span` chunk iterations
-  const int my_units = (p.nunits > (int)blockIdx.x) ? (p.nunits - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int total_it = my_units * p.span;
+  // this CTA's contiguous range of chunk iterations
+  const long long it_lo = p.total * (long long)blockIdx.x / (long long)gridDim.x;
+  const long long it_hi = p.total * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
+  const int total_it = (int)(it_hi - it_lo);
 
   if (warp == kPdWarps)
   {
     // ===== producer warp =====
-    PdCursor cx_cur, pf_cur;
-    cx_cur.init(p, (int)blockIdx.x);
-    pf_cur.init(p, (int)blockIdx.x);
-    int pf_it = 0;
-    auto prefetch_phi = [&]() {  // 64 rows x 1 KB of the chunk at pf_cur, two rows per lane
-      const int col0 = pf_cur.chunk(p) * kPdChunk;
-      if (col0 < p.nx)
-      {
-        const uint32_t bytes = (uint32_t)min(kPdChunk, p.nx - col0) * 8u;
-#pragma unroll
-        for (int r = 0; r < 2; r++)
-        {
-          const int row = pf_cur.rb * kPdRows + lane + 32 * r;
-          if (row < p.ny) tma_prefetch_l2(p.phi + (size_t)row * p.nx + col0, bytes);
-        }
-      }
-      pf_cur.advance(p, (int)gridDim.x);
-      pf_it++;
-    };
-    while (pf_it < min(p.ahead, total_it)) prefetch_phi();
+    // Besides feeding the C_x ring it keeps a window of the band `ahead` chunks in
+    // front of the consumers warm in L2 (cp.async.bulk.prefetch.L2), extended in
+    // pieces of `pflen` chunks per row so one instruction covers several KB.
+    PdCursor cx_cur;
+    cx_cur.init(p, it_lo);
+    int pf_rb = -1, pf_k = 0;
     for (int it = 0; it < total_it; it++)
     {
       const int s = it % kPdStages;
       if (it >= kPdStages) mbar_wait(&empty[s], ((it / kPdStages) - 1) & 1);
       if (lane == 0)
       {
-        mbar_expect_tx(&full[s], kPdChunkBytes);
-        tma_bulk_g2s(cxs0 + s * (kPdChunkBytes / 8), p.cxp + (size_t)cx_cur.chunk(p) * kPdChunk * kPdPitch,
-                     kPdChunkBytes, &full[s]);
+        mbar_expect_tx(&full[s], G::kChunkBytes);
+        tma_bulk_g2s(cxs0 + s * (G::kChunkBytes / 8), p.cxp + (size_t)cx_cur.k * CH * kPdPitch, G::kChunkBytes,
+                     &full[s]);
       }
-      cx_cur.advance(p, (int)gridDim.x);
-      if (p.ahead > 0 && pf_it < total_it) prefetch_phi();
+      if (p.ahead > 0)
+      {
+        if (cx_cur.rb != pf_rb)
+        {
+          pf_rb = cx_cur.rb;
+          pf_k = cx_cur.k;
+        }
+        while (pf_k < min(p.nchunks, cx_cur.k + p.ahead))
+        {
+          const int col0 = pf_k * CH, col1 = min((pf_k + p.pflen) * CH, p.ncols);
+          pf_k += p.pflen;
+          if (col1 <= col0) continue;
+#pragma unroll
+          for (int r = 0; r < 2; r++)
+          {
+            const int row = pf_rb * kPdRows + lane + 32 * r;
+            if (row < p.ny)
+            {
+              const double* base = p.phi + (size_t)row * p.nx;
+              tma_prefetch_l2(base + col0, (uint32_t)(col1 - col0) * 8u);
+              if (FOLD) tma_prefetch_l2(base + (p.nx - col1), (uint32_t)(col1 - col0) * 8u);
+            }
+          }
+        }
+      }
+      cx_cur.advance(p);
     }
     return;
   }
@@ -229,56 +280,73 @@ __global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmma
   for (int t = 0; t < 4; t++) T[t][0] = T[t][1] = 0.0;
 
   PdCursor ld_cur;  // the chunk whose Phi is being LOADED (one iteration ahead of the compute)
-  ld_cur.init(p, (int)blockIdx.x);
-  int cur_rb = ld_cur.rb;
+  ld_cur.init(p, it_lo);
+  int cur_rb = ld_cur.rb, cur_k = ld_cur.k;  // the chunk being computed
 
   // Phi fragments are double-buffered in registers: the 32-byte loads of chunk
   // it + 1 are all issued BEFORE the DMMAs of chunk it (ptxas otherwise sinks
   // them behind the last use of a shared window and exposes the full latency).
-  double va[4][4], vb[4][4];
+  // [.][0]: the lane's 4 columns of group grp; [.][1] (fold): their mirror columns.
+  double va[GR][NV][4], vb[GR][NV][4];
+  auto load_chunk = [&](const int row, const int col0, const bool row_ok, double (&v)[GR][NV][4]) {
+    const double* src = p.phi + (size_t)row * p.nx;
+#pragma unroll
+    for (int grp = 0; grp < GR; grp++)
+    {
+      const int c = col0 + 16 * grp + 4 * q;  // first of this lane's 4 logical columns
+      const bool ok = row_ok && c < p.ncols;
+      ldg_stream4(src + c, ok, v[grp][0]);
+      if (FOLD) ldg_stream4(src + (p.nx - 4 - c), ok, v[grp][NV - 1]);  // columns nx-1-c-3 .. nx-1-c
+    }
+  };
   if (total_it > 0)
   {
-    const int row = ld_cur.rb * kPdRows + rg * 8 + g, col0 = ld_cur.chunk(p) * kPdChunk + half * 64;
-    const double* src = p.phi + (size_t)row * p.nx + col0 + 4 * q;
-#pragma unroll
-    for (int grp = 0; grp < 4; grp++)
-      ldg_stream4(src + 16 * grp, row < p.ny && col0 + 16 * grp + 4 * q < p.nx, va[grp]);
-    ld_cur.advance(p, (int)gridDim.x);
+    const int row = ld_cur.rb * kPdRows + rg * 8 + g;
+    load_chunk(row, ld_cur.k * CH + half * (CH / 2), row < p.ny, va);
+    ld_cur.advance(p);
   }
 
-  int k_in_unit = 0;
-  auto iteration = [&](const int it, double (&vc)[4][4], double (&vn)[4][4]) {
+  auto iteration = [&](const int it, double (&vc)[GR][NV][4], double (&vn)[GR][NV][4]) {
     const int s = it % kPdStages;
     const bool has_next = it + 1 < total_it;
-    const int nrow = ld_cur.rb * kPdRows + rg * 8 + g, ncol0 = ld_cur.chunk(p) * kPdChunk + half * 64;
+    const int nrow = ld_cur.rb * kPdRows + rg * 8 + g, ncol0 = ld_cur.k * CH + half * (CH / 2);
     const int next_rb = ld_cur.rb;
-    const double* nsrc = p.phi + (size_t)nrow * p.nx + ncol0 + 4 * q;
-    const bool nrow_ok = has_next && nrow < p.ny;
-    if (has_next) ld_cur.advance(p, (int)gridDim.x);
-#pragma unroll
-    for (int grp = 0; grp < 4; grp++)
-      ldg_stream4(nsrc + 16 * grp, nrow_ok && ncol0 + 16 * grp + 4 * q < p.nx, vn[grp]);
+    if (has_next) ld_cur.advance(p);
+    load_chunk(nrow, ncol0, has_next && nrow < p.ny, vn);
 
     mbar_wait(&full[s], (it / kPdStages) & 1);
-    const double* bbase = cxs0 + s * (kPdChunkBytes / 8) + (half * 64 + q) * kPdPitch + g;
+    const double* bbase = cxs0 + s * (G::kChunkBytes / 8) + (half * (CH / 2) + q) * kPdPitch + g;
 #pragma unroll
-    for (int grp = 0; grp < 4; grp++)
+    for (int grp = 0; grp < GR; grp++)
 #pragma unroll
       for (int st = 0; st < 4; st++)
       {
-        const double a = vc[grp][st];
         const double* brow = bbase + (16 * grp + 4 * st) * kPdPitch;
+        if (FOLD)
+        {
+          // column c + st pairs with its mirror nx-1-c-st = (nx-4-c) + (3-st)
+          const double lo = vc[grp][0][st], hi = vc[grp][NV - 1][3 - st];
+          const double ev = lo + hi, od = lo - hi;
+          dmma884(T[0][0], T[0][1], ev, brow[0]);   // orders 0, 2, .., 14
+          dmma884(T[1][0], T[1][1], ev, brow[8]);   // orders 16, .., 30
+          dmma884(T[2][0], T[2][1], od, brow[16]);  // orders 1, 3, .., 15
+          dmma884(T[3][0], T[3][1], od, brow[24]);  // orders 17, .., 31
+        }
+        else
+        {
+          const double a = vc[grp][0][st];
 #pragma unroll
-        for (int t = 0; t < 4; t++) dmma884(T[t][0], T[t][1], a, brow[8 * t]);
+          for (int t = 0; t < 4; t++) dmma884(T[t][0], T[t][1], a, brow[8 * t]);
+        }
       }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the C_x stage
 
-    if (++k_in_unit == p.span)
+    if (++cur_k == p.nchunks || !has_next)
     {
-      // Unit finished.  Sum the two column halves' tiles in the stage
-      // (C layout: row 8*rg + g, cols 8t + 2q + e), then fold with C_y.
-      k_in_unit = 0;
+      // End of the band (or of this CTA's range).  Sum the two column halves' tiles in
+      // the stage (C layout: row 8*rg + g, cols 8t + 2q + e), then fold with C_y.
+      cur_k = 0;
       double* trow = tstage + (rg * 8 + g) * kPdStagePitch + 2 * q;
       if (half == 0)
       {
@@ -325,6 +393,7 @@ __global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmma
   }
 
   {
+    // with the fold the partial's columns are in [even orders | odd orders] order; phik_finalize undoes it
     const int m = warp >> 2, t = warp & 3;
     double* out = p.parts + (size_t)blockIdx.x * 1024 + (8 * m + g) * 32 + 8 * t + 2 * q;
     out[0] = P[0];
@@ -332,12 +401,13 @@ __global__ void __launch_bounds__(kPdThreads, 1) phik_dmma_kernel(const PhikDmma
   }
 }
 
-// Picks the column span per unit so that the units fill the grid evenly while
-// the per-unit epilogue stays small; returns the number of partial blocks
-// written (= grid size) or -1 on a launch failure.
-inline int phik_dmma_launch(const double* phi, int nx, int ny, const double* cxp, const double* cy, double* parts,
-                            int max_parts, cudaStream_t stream)
+// Launches one persistent CTA per SM (fewer when there is less work than that);
+// returns the number of partial blocks written (= grid size) or -1 on a launch failure.
+template <bool FOLD>
+inline int phik_dmma_launch_t(const double* phi, int nx, int ny, const double* cxp, const double* cy, double* parts,
+                              int max_parts, cudaStream_t stream)
 {
+  using G = PdGeom<FOLD>;
   PhikDmmaParams p{};
   p.phi = phi;
   p.cxp = cxp;
@@ -345,42 +415,38 @@ inline int phik_dmma_launch(const double* phi, int nx, int ny, const double* cxp
   p.parts = parts;
   p.nx = nx;
   p.ny = ny;
-  p.nchunks = (nx + kPdChunk - 1) / kPdChunk;
+  p.ncols = FOLD ? nx / 2 : nx;
+  p.nchunks = (p.ncols + G::kChunk - 1) / G::kChunk;
   {
-    static const int ahead = getenv("EB_PHIK_AHEAD") ? atoi(getenv("EB_PHIK_AHEAD")) : kPdAhead;
-    p.ahead = ahead;
+    // L2 prefetch window / piece of the producer warp, in chunk iterations (tuned on B200, 8192^2, nb = 32)
+    static const int ahead = getenv("EB_PHIK_AHEAD") ? atoi(getenv("EB_PHIK_AHEAD")) : -1;
+    static const int pflen = getenv("EB_PHIK_PFLEN") ? atoi(getenv("EB_PHIK_PFLEN")) : -1;
+    p.ahead = ahead >= 0 ? ahead : kPdAhead;
+    p.pflen = pflen > 0 ? pflen : kPdPfLen;
   }
   const int row_blocks = (ny + kPdRows - 1) / kPdRows;
-  const int grid_max = max_parts;
-  double best = -1.0;
-  for (int span = 1; span <= p.nchunks; span++)
-  {
-    const int nspans = (p.nchunks + span - 1) / span;
-    const long long units = (long long)row_blocks * nspans;
-    const int grid = (int)std::min<long long>(units, grid_max);
-    const long long waves = (units + grid - 1) / grid;
-    const double balance = (double)units / (double)(waves * grid);      // tail efficiency
-    const double padding = (double)p.nchunks / (double)(nspans * span);  // wasted chunk slots
-    const double epilogue = 1.0 / (1.0 + 32.0 / (span * (double)kPdChunk) + 0.02 / span);
-    const double score = balance * padding * epilogue * ((double)grid / grid_max);
-    if (score > best)
-    {
-      best = score;
-      p.span = span;
-      p.nspans = nspans;
-      p.nunits = (int)units;
-    }
-  }
-  const int grid = std::min(p.nunits, grid_max);
-  static bool configured = false;
+  p.total = (long long)row_blocks * p.nchunks;
+  const int grid = (int)std::min<long long>(p.total, max_parts);
+  static bool configured = false;  // per instantiation
   if (!configured)
   {
-    if (cudaFuncSetAttribute(phik_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(phik_dmma_kernel<FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes) !=
+        cudaSuccess)
       return -1;
     configured = true;
   }
-  phik_dmma_kernel<<<grid, kPdThreads, kPdSmemBytes, stream>>>(p);
+  phik_dmma_kernel<FOLD><<<grid, kPdThreads, G::kSmemBytes, stream>>>(p);
   if (cudaGetLastError() != cudaSuccess) return -1;
   return grid;
 }
+
+inline int phik_dmma_launch(const double* phi, int nx, int ny, const double* cxp, const double* cy, double* parts,
+                            int max_parts, bool fold, cudaStream_t stream)
+{
+  return fold ? phik_dmma_launch_t<true>(phi, nx, ny, cxp, cy, parts, max_parts, stream) :
+                phik_dmma_launch_t<false>(phi, nx, ny, cxp, cy, parts, max_parts, stream);
+}
+
+// the fold needs the mirrored 32-byte loads aligned (nx % 8 == 0 keeps nx / 2 a multiple of 4)
+inline bool phik_fold_shape_ok(int nx) { return nx % 8 == 0; }
 }  // namespace eb

@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(256) phik_stage2_simple(const double* __restri
 }
 
 // sums `nparts` partial 32x32 blocks in a fixed order (deterministic) and
-// normalises: phik[ky*nb + kx] = raw[ky][kx] / raw[0][0]
-__global__ void __launch_bounds__(1024) phik_finalize(const double* __restrict__ parts, int nparts, int nb,
+// normalises: phik[ky*nb + kx] = raw[ky][kx] / raw[0][0].  fold: the partials'
+// columns are in the tile kernel's [even orders | odd orders] order.
+__global__ void __launch_bounds__(1024) phik_finalize(const double* __restrict__ parts, int nparts, int nb, int fold,
                                                       double* __restrict__ phik, double* __restrict__ phi_sum,
                                                       double* __restrict__ raw)
 {
@@ -98,10 +99,11 @@ __global__ void __launch_bounds__(1024) phik_finalize(const double* __restrict__
   const int t = threadIdx.x;
   double s = 0.0;
   for (int pth = 0; pth < nparts; pth++) s += parts[(size_t)pth * 1024 + t];
-  if (t == 0) total = s;
+  if (t == 0) total = s;  // order (0, 0) sits at column 0 either way
   __syncthreads();
-  const int ky = t >> 5, kx = t & 31;
-  if (raw) raw[t] = (ky < nb && kx < nb) ? s : 0.0;
+  const int ky = t >> 5, col = t & 31;
+  const int kx = fold ? (col < 16 ? 2 * col : 2 * (col - 16) + 1) : col;
+  if (raw) raw[ky * 32 + kx] = (ky < nb && kx < nb) ? s : 0.0;
   if (phik && ky < nb && kx < nb) phik[ky * nb + kx] = s / total;
   if (t == 0 && phi_sum) *phi_sum = total;
 }

@@ -178,8 +178,13 @@ eb_status eb_phik_plan_create_rows(int device, int nx, int ny_total, int row_beg
                                    double resolution, double lx, double ly, int nb, eb_phik_plan **out);
 void eb_phik_plan_destroy(eb_phik_plan *p);
 eb_status eb_phik_plan_set_stream(eb_phik_plan *p, void *cuda_stream);
-/* algo: 0 = auto, 1 = simple (any shape), 2 = DMMA tiles (TMA-fed) */
+/* algo: 0 = auto, 1 = simple (any shape), 2 = DMMA tiles (TMA-fed; mirror-folded when the
+ * grid's cosine table is symmetric, see eb_phik_plan_fold), 3 = DMMA tiles without the fold */
 eb_status eb_phik_plan_set_algo(eb_phik_plan *p, int algo);
+/* fold = 1 when the plan's grid allows the mirror fold (x_j + x_{nx-1-j} == lx to rounding, so
+ * cos(k pi x / lx) is (-1)^k-symmetric and half the contraction suffices); deviation = the
+ * measured asymmetry of the table, which bounds the fold's coefficient error (taken iff <= 1e-10) */
+eb_status eb_phik_plan_fold(const eb_phik_plan *p, int *fold, double *deviation);
 eb_status eb_phik_execute_dev(eb_phik_plan *p, const double *phi_dev, double *phik_dev,
                               double *phi_sum_dev);
 eb_status eb_phik_execute_host(eb_phik_plan *p, const double *phi, double *phik, double *phi_sum);

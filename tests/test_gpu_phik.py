@@ -34,6 +34,10 @@ def gaussian_mixture(rng, nx, ny, res, ng=8):
     (1024, 520, 32, 2),
     (512, 64, 7, 2),
     (1280, 1100, 24, 0),  # auto -> tile kernel
+    (1024, 520, 32, 3),   # tile kernel with the mirror fold switched off
+    (136, 70, 32, 2),     # fold, nx / 2 = 68: ragged folded chunk
+    (136, 70, 32, 3),
+    (2056, 130, 31, 2),   # fold, several units per row block, odd basis count
 ])
 def test_phik_matches_oracle(nx, ny, nb, algo):
     from ergodic_exploration_b200 import PhikPlan
@@ -61,6 +65,33 @@ def test_phik_arbitrary_density_not_separable():
     got = PhikPlan(nx, ny, res, lx, ly, nb).execute(phi)
     want, _ = Oracle.phik_from_grid(phi, res, lx, ly, nb)
     assert_coeff_close(got, want, "random density")
+
+
+def test_phik_mirror_fold_gate_and_bound():
+    """the fold is taken only on grids whose cosine table is mirror-symmetric
+    (lx == (nx - 1) res); folded and unfolded tile kernels agree to the measured
+    table asymmetry; a grid with another lx falls back and still matches the oracle"""
+    from ergodic_exploration_b200 import PhikPlan
+
+    rng = np.random.default_rng(77)
+    nx, ny, nb, res = 1024, 200, 32, 0.1
+    phi = rng.random((ny, nx)) ** 3  # no symmetry of its own
+    lx, ly = (nx - 1) * res, (ny - 1) * res
+    folded, plain = PhikPlan(nx, ny, res, lx, ly, nb, algo=2), PhikPlan(nx, ny, res, lx, ly, nb, algo=3)
+    ok, dev = folded.fold()
+    assert ok and dev <= 1e-10
+    a, b = folded.execute(phi), plain.execute(phi)
+    assert np.max(np.abs(a - b)) <= max(4.0 * dev, 1e-13)
+    want, _ = Oracle.phik_from_grid(phi, res, lx, ly, nb)
+    assert_coeff_close(a, want, "folded")
+    assert_coeff_close(b, want, "unfolded")
+    # the reference's configTarget grid can overshoot: lx = 102.33 -> nx = round(lx / res) + 1 = 1024, last point 102.3
+    lx2 = 102.33
+    skew = PhikPlan(nx, ny, res, lx2, ly, nb, algo=2)
+    ok2, dev2 = skew.fold()
+    assert not ok2 and dev2 > 1e-10
+    want2, _ = Oracle.phik_from_grid(phi, res, lx2, ly, nb)
+    assert_coeff_close(skew.execute(phi), want2, "asymmetric grid -> unfolded")
 
 
 def test_phik_linearity_large():
