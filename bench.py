@@ -368,7 +368,7 @@ def run_ours(args, wl, rank, world, local_rank):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_traffic.json"))).get(args.workload)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_traffic.json")))[args.workload]["bytes"]
     except Exception:
         pass
     line = {
@@ -506,7 +506,7 @@ def run_phik(args, rank, world, local_rank):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_traffic.json"))).get("c3")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_traffic.json")))["c3"]["bytes"]
     except Exception:
         pass
     sec = ms * 1e-3 * world  # per-GPU seconds of kernel work behind one step (row shards run concurrently)

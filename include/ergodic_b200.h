@@ -214,6 +214,36 @@ eb_status eb_basis_spatial_coeff_host(int device, double lx, double ly, int nb, 
 eb_status eb_target_fill_host(int device, int ng, const double *mu, const double *sigma,
                               const double *trans, const double *phi_grid, long long G, double *phi_vals);
 
+/* ---- occupancy-grid collision checks ----------------
+ * Batched Collision::collisionCheck (collision.cpp:126-143) and validate_control
+ * (numerics.hpp:312-330) -- the call the exploration loop makes on the twist control()
+ * returns, every tick (exploration.hpp:238).  One occupancy grid (GridMap: int8 cells,
+ * row-major, i = y row / j = x column, grid.hpp:52) is shared by the whole batch. */
+typedef struct eb_grid eb_grid;
+typedef struct eb_collision {
+  double boundary_radius;    /* collision.hpp:95-96 */
+  double search_radius;
+  double obstacle_threshold;
+  double occupied_threshold;
+} eb_collision;
+/* copies ysize x xsize cells to the device; resolution / xmin / ymin as GridMap (grid.cpp:46-61) */
+eb_status eb_grid_create(int device, const signed char *data, unsigned int xsize, unsigned int ysize,
+                         double resolution, double xmin, double ymin, eb_grid **out);
+eb_status eb_grid_update(eb_grid *g, const signed char *data); /* GridMap::update, same geometry */
+void eb_grid_destroy(eb_grid *g);
+eb_status eb_grid_set_stream(eb_grid *g, void *cuda_stream);
+/* EB_ERR_INVALID_ARGUMENT where the Collision constructor throws (collision.cpp:46-64) */
+/* hit[i] = 1 when pose i (x, y, theta; 3 x count) collides */
+eb_status eb_collision_check_host(eb_grid *g, const eb_collision *c, const double *poses, int count, int *hit);
+eb_status eb_collision_check_dev(eb_grid *g, const eb_collision *c, const double *poses_dev, int count,
+                                 int *hit_dev);
+/* valid[i] = 1 when twist u_i held for |horizon / dt| steps of dt from x0_i stays collision free */
+eb_status eb_validate_control_host(eb_grid *g, const eb_collision *c, const double *x0, const double *u, int count,
+                                   double dt, double horizon, int *valid);
+eb_status eb_validate_control_dev(eb_grid *g, const eb_collision *c, const double *x0_dev, const double *u_dev,
+                                  int count, double dt, double horizon, int *valid_dev);
+long long eb_grid_launch_count(const eb_grid *g);
+
 /* ---- measurement helper --------------------------------------------------
  * Measured FP64 throughput of the device (TFLOP/s, 2 flop per FMA): a
  * register-resident DFMA loop and an mma.sync m8n8k4 f64 (DMMA) loop.  Used

@@ -54,6 +54,83 @@ void eo_integrate_twist(const double x[3], const double u[3], double dt, double 
 }
 
 /* ------------------------------------------------------------------------ */
+/* occupancy-grid collision checking                                        */
+/* ------------------------------------------------------------------------ */
+
+/* Collision::checkCell collision.cpp:217-244 without the closest-obstacle book-keeping
+ * (cfg.sqrd_obs, dx, dy feed minDistance / minDirection only).  cj, ci are `unsigned int`
+ * in the reference: negative coordinates wrap and fail GridMap::gridBounds (grid.cpp:96-100). */
+static int check_cell(const eo_grid *g, const eo_collision *c, int cx, int cy, int r_col,
+                      unsigned int cj, unsigned int ci)
+{
+  if (!(ci <= g->ysize - 1u && cj <= g->xsize - 1u)) return 0;
+  /* GridMap::getCell grid.cpp:177-184: int8 cell / 100.0 */
+  const double cell = (double)g->data[(size_t)ci * g->xsize + cj] / 100.0;
+  if (cell < c->occupied_threshold) return 0;
+  const unsigned int dj = (unsigned int)cx - cj, di = (unsigned int)cy - ci;
+  const int sqrd_obs = (int)(dj * dj + di * di);
+  return sqrd_obs <= r_col * r_col;
+}
+
+/* Collision::bresenhamCircle collision.cpp:169-215 */
+static int bresenham_circle(const eo_grid *g, const eo_collision *c, int cx, int cy, int r_col, int r)
+{
+  int x = -r, y = 0, err = 2 - 2 * r;
+  while (x < 0) {
+    if (check_cell(g, c, cx, cy, r_col, (unsigned int)(cx - x), (unsigned int)(cy + y))) return 1;
+    if (check_cell(g, c, cx, cy, r_col, (unsigned int)(cx - y), (unsigned int)(cy - x))) return 1;
+    if (check_cell(g, c, cx, cy, r_col, (unsigned int)(cx + x), (unsigned int)(cy - y))) return 1;
+    if (check_cell(g, c, cx, cy, r_col, (unsigned int)(cx + y), (unsigned int)(cy + x))) return 1;
+    r = err;
+    if (r <= y) {
+      y++;
+      err += 2 * y + 1;
+    }
+    if (r > x || err > y) {
+      x++;
+      err += 2 * x + 1;
+    }
+  }
+  return 0;
+}
+
+int eo_collision_check(const eo_grid *g, const eo_collision *c, const double pose[3])
+{
+  /* GridMap::world2Grid grid.cpp:143-160.  The reference casts floor() to unsigned int and
+   * then to int (CollisionConfig); for a pose left of / below the map that is a wrap-around
+   * on x86-64, i.e. the plain signed floor, which is what is restated here. */
+  long long jl = (long long)floor((pose[0] - g->xmin) / g->resolution);
+  long long il = (long long)floor((pose[1] - g->ymin) / g->resolution);
+  unsigned int j = (unsigned int)jl, i = (unsigned int)il;
+  if (j == g->xsize) j--;
+  if (i == g->ysize) i--;
+  const int cx = (int)j, cy = (int)i;
+  /* collision.cpp:130-133 */
+  const int r_bnd = (int)floor(c->boundary_radius / g->resolution);
+  const int r_col = (int)floor((c->boundary_radius + c->obstacle_threshold) / g->resolution);
+  const int r_max = (int)floor(c->search_radius / g->resolution);
+  /* Collision::search collision.cpp:150-167 */
+  for (int r = r_bnd; r <= r_max; r++)
+    if (bresenham_circle(g, c, cx, cy, r_col, r)) return 1;
+  return 0;
+}
+
+int eo_validate_control(const eo_grid *g, const eo_collision *c, const double x0[3],
+                        const double u[3], double dt, double horizon)
+{
+  double x[3] = { x0[0], x0[1], x0[2] };
+  const unsigned int steps = (unsigned int)fabs(horizon / dt);
+  for (unsigned int i = 0; i < steps; i++) {
+    double xn[3];
+    eo_integrate_twist(x, u, dt, xn);
+    xn[2] = eo_normalize_angle_pi(xn[2]);
+    memcpy(x, xn, sizeof(x));
+    if (eo_collision_check(g, c, x)) return 0;
+  }
+  return 1;
+}
+
+/* ------------------------------------------------------------------------ */
 /* models                                                                   */
 /* ------------------------------------------------------------------------ */
 

@@ -108,6 +108,24 @@ void eo_phik_from_grid(const double *phi, int nx, int ny, double resolution, dou
                        double ly, int nb, double *phik, double *phi_sum);
 
 /* ---- ErgodicControl (ergodic_control.hpp) ------------------------------ */
+/* ---- occupancy-grid collision checking ------------- */
+/* GridMap geometry (grid.hpp / grid.cpp): int8 cells, row-major (i = y row, j = x column) */
+typedef struct eo_grid {
+  const signed char *data; /* ysize x xsize */
+  unsigned int xsize, ysize;
+  double resolution, xmin, ymin;
+} eo_grid;
+/* Collision (collision.hpp:85-165, collision.cpp:46-64) */
+typedef struct eo_collision {
+  double boundary_radius, search_radius, obstacle_threshold, occupied_threshold;
+} eo_collision;
+/* Collision::collisionCheck collision.cpp:126-143 (+ search :150-167, bresenhamCircle
+ * :169-215, checkCell :217-244, GridMap::world2Grid grid.cpp:143-160); 1 = collision */
+int eo_collision_check(const eo_grid *g, const eo_collision *c, const double pose[3]);
+/* validate_control numerics.hpp:312-330; 1 = collision free */
+int eo_validate_control(const eo_grid *g, const eo_collision *c, const double x0[3],
+                        const double u[3], double dt, double horizon);
+
 typedef struct eo_controller eo_controller;
 
 /* ctor :188-222.  Rinv is 3x3 column-major.  Returns NULL when steps==1

@@ -320,6 +320,45 @@ class Oracle:
         return ph, s.value
 
 
+    # ---- occupancy-grid collision checking ------------
+    class _Grid(C.Structure):
+        _fields_ = [("data", C.c_void_p), ("xsize", C.c_uint), ("ysize", C.c_uint),
+                    ("resolution", C.c_double), ("xmin", C.c_double), ("ymin", C.c_double)]
+
+    class _Collision(C.Structure):
+        _fields_ = [("boundary_radius", C.c_double), ("search_radius", C.c_double),
+                    ("obstacle_threshold", C.c_double), ("occupied_threshold", C.c_double)]
+
+    @classmethod
+    def _grid_args(cls, data, res, xmin, ymin, col):
+        data = np.ascontiguousarray(data, dtype=np.int8)
+        g = cls._Grid(data.ctypes.data, data.shape[1], data.shape[0], res, xmin, ymin)
+        c = cls._Collision(*[float(v) for v in col])
+        return data, g, c
+
+    @classmethod
+    def collision_check(cls, data, res, xmin, ymin, col, poses):
+        """col = (boundary_radius, search_radius, obstacle_threshold, occupied_threshold); -> int array, 1 = hit"""
+        data, g, c = cls._grid_args(data, res, xmin, ymin, col)
+        poses, _ = _d(poses)
+        poses = poses.reshape(-1, 3)
+        f = cls.lib().eo_collision_check
+        f.argtypes = [C.c_void_p, C.c_void_p, _dp]
+        return np.array([f(C.byref(g), C.byref(c), poses[i].ctypes.data_as(_dp)) for i in range(len(poses))],
+                        dtype=np.int32)
+
+    @classmethod
+    def validate_control(cls, data, res, xmin, ymin, col, x0, u, dt, horizon):
+        """-> int array, 1 = collision free (numerics.hpp:312-330)"""
+        data, g, c = cls._grid_args(data, res, xmin, ymin, col)
+        x0, _ = _d(x0); u, _ = _d(u)
+        x0, u = x0.reshape(-1, 3), u.reshape(-1, 3)
+        f = cls.lib().eo_validate_control
+        f.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, C.c_double, C.c_double]
+        return np.array([f(C.byref(g), C.byref(c), x0[i].ctypes.data_as(_dp), u[i].ctypes.data_as(_dp), dt, horizon)
+                         for i in range(len(x0))], dtype=np.int32)
+
+
 class RefLib:
     """The unmodified reference, compiled against the shim."""
 
@@ -474,3 +513,31 @@ class RefLib:
         cls.lib().ref_spatial_coeff(C.c_double(lx), C.c_double(ly), C.c_int(nb), pv, pg,
                                     C.c_longlong(vals.size), ph.ctypes.data_as(_dp))
         return ph
+
+    # ---- occupancy-grid collision checking: the reference's own GridMap / Collision ----
+    @classmethod
+    def collision_check(cls, data, res, xmin, ymin, col, poses):
+        data = np.ascontiguousarray(data, dtype=np.int8)
+        poses, pp = _d(poses)
+        n = poses.size // 3
+        hit = np.zeros(n, dtype=np.int32)
+        f = cls.lib().ref_collision_check_many
+        f.argtypes = [C.c_void_p, C.c_uint, C.c_uint] + [C.c_double] * 7 + [_dp, C.c_int, _ip]
+        if f(data.ctypes.data, data.shape[1], data.shape[0], res, xmin, ymin, *[float(v) for v in col], pp, n,
+             hit.ctypes.data_as(_ip)) != 0:
+            raise ValueError(cls.lib().ref_last_error().decode())
+        return hit
+
+    @classmethod
+    def validate_control(cls, data, res, xmin, ymin, col, x0, u, dt, horizon):
+        data = np.ascontiguousarray(data, dtype=np.int8)
+        x0, px = _d(x0); u, pu = _d(u)
+        n = x0.size // 3
+        valid = np.zeros(n, dtype=np.int32)
+        f = cls.lib().ref_validate_control_many
+        f.argtypes = [C.c_void_p, C.c_uint, C.c_uint] + [C.c_double] * 7 + [_dp, _dp, C.c_int, C.c_double,
+                                                                             C.c_double, _ip]
+        if f(data.ctypes.data, data.shape[1], data.shape[0], res, xmin, ymin, *[float(v) for v in col], px, pu, n,
+             dt, horizon, valid.ctypes.data_as(_ip)) != 0:
+            raise ValueError(cls.lib().ref_last_error().decode())
+        return valid

@@ -410,4 +410,52 @@ int ref_control_many(void** hs, int count, double xmin, double xmax, double ymin
     return -1;
   }
 }
+
+// ---- occupancy-grid collision checking (collision.cpp, numerics.hpp:312-330) ----
+// The grid is rebuilt through the reference's own GridMap constructor
+// (grid.cpp:46-61): xmax / ymax are chosen so that axis_length() returns xsize / ysize.
+static ee::GridMap occupancy_grid(const signed char* data, unsigned xsize, unsigned ysize, double res, double xmin,
+                                  double ymin)
+{
+  const double xmax = ee::axis_upper(xmin, res, xsize), ymax = ee::axis_upper(ymin, res, ysize);
+  return ee::GridMap(xmin, xmax, ymin, ymax, res, ee::GridData(data, data + size_t(xsize) * ysize));
+}
+
+int ref_collision_check_many(const signed char* data, unsigned xsize, unsigned ysize, double res, double xmin,
+                             double ymin, double boundary_radius, double search_radius, double obstacle_threshold,
+                             double occupied_threshold, const double* poses, int count, int* hit)
+{
+  try
+  {
+    const ee::GridMap grid = occupancy_grid(data, xsize, ysize, res, xmin, ymin);
+    const ee::Collision col(boundary_radius, search_radius, obstacle_threshold, occupied_threshold);
+    for (int i = 0; i < count; i++) hit[i] = col.collisionCheck(grid, v3(poses + 3 * i)) ? 1 : 0;
+    return 0;
+  }
+  catch (const std::exception& e)
+  {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+int ref_validate_control_many(const signed char* data, unsigned xsize, unsigned ysize, double res, double xmin,
+                              double ymin, double boundary_radius, double search_radius, double obstacle_threshold,
+                              double occupied_threshold, const double* x0, const double* u, int count, double dt,
+                              double horizon, int* valid)
+{
+  try
+  {
+    const ee::GridMap grid = occupancy_grid(data, xsize, ysize, res, xmin, ymin);
+    const ee::Collision col(boundary_radius, search_radius, obstacle_threshold, occupied_threshold);
+    for (int i = 0; i < count; i++)
+      valid[i] = ee::validate_control(col, grid, v3(x0 + 3 * i), v3(u + 3 * i), dt, horizon) ? 1 : 0;
+    return 0;
+  }
+  catch (const std::exception& e)
+  {
+    g_err = e.what();
+    return -1;
+  }
+}
 }  // extern "C"
