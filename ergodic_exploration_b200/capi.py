@@ -46,6 +46,13 @@ class EbConfig(C.Structure):
     ]
 
 
+class EbCollision(C.Structure):
+    """struct eb_collision (include/ergodic_b200.h)"""
+
+    _fields_ = [("boundary_radius", C.c_double), ("search_radius", C.c_double),
+                ("obstacle_threshold", C.c_double), ("occupied_threshold", C.c_double)]
+
+
 class ErgodicB200Error(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"[eb_status {status}] {message}")
@@ -110,6 +117,15 @@ SIGNATURES = {
     "eb_basis_spatial_coeff_host": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, _vp, _vp, C.c_longlong, _vp]),
     "eb_target_fill_host": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_longlong, _vp]),
     "eb_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
+    "eb_grid_create": (C.c_int, [C.c_int, _vp, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.POINTER(_vp)]),
+    "eb_grid_update": (C.c_int, [_vp, _vp]),
+    "eb_grid_destroy": (None, [_vp]),
+    "eb_grid_set_stream": (C.c_int, [_vp, _vp]),
+    "eb_grid_launch_count": (C.c_longlong, [_vp]),
+    "eb_collision_check_host": (C.c_int, [_vp, C.POINTER(EbCollision), _vp, C.c_int, _vp]),
+    "eb_collision_check_dev": (C.c_int, [_vp, C.POINTER(EbCollision), _vp, C.c_int, _vp]),
+    "eb_validate_control_host": (C.c_int, [_vp, C.POINTER(EbCollision), _vp, _vp, C.c_int, C.c_double, C.c_double, _vp]),
+    "eb_validate_control_dev": (C.c_int, [_vp, C.POINTER(EbCollision), _vp, _vp, C.c_int, C.c_double, C.c_double, _vp]),
 }
 
 _lib = None

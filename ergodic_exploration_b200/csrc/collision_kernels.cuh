@@ -14,13 +14,13 @@
 //  * Radius pruning.  checkCell reports a collision only for cells with
 //    dx^2 + dy^2 <= r_col^2, and every cell this circle walk emits for radius r
 //    lies farther than r - 1/2 from the centre (checked exhaustively for
-//    r < kPruneVerified in tests/test_collision_oracle.py), so circles with
+//    r < kPruneVerified in tests/test_collision_cpu.py), so circles with
 //    r > r_col can never hit: the search stops at min(r_max, r_col) instead of
 //    r_max.  The closest-obstacle book-keeping of checkCell (cfg.sqrd_obs, dx, dy)
 //    feeds minDistance / minDirection only and is not computed.
 //  * world2Grid casts floor() to unsigned (undefined for poses left of / below
 //    the map); the x86-64 behaviour -- wrap-around, i.e. the signed floor -- is
-//    what the oracle restates and what is implemented here.
+//    what the CPU checker under tests restates and what is implemented here.
 // The pose chain of validate_control uses explicitly rounded multiplies / adds in
 // the reference's association order; sin / cos come from the CUDA library, so a
 // pose can differ from glibc's by an ulp or two (a cell index could differ only

@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include "collision_kernels.cuh"
 #include "phik_dmma.cuh"
 #include "phik_kernels.cuh"
 #include "solve_kernel.cuh"
@@ -1069,6 +1070,189 @@ eb_status eb_target_fill_host(int device, int ng, const double* mu, const double
   eb::vector_div_kernel<<<blocks, 256>>>(dv.p, G, dt.p);  // target.cpp:87
   EB_CUDA(cudaGetLastError());
   EB_CUDA(cudaMemcpy(phi_vals, dv.p, sizeof(double) * G, cudaMemcpyDeviceToHost));
+  return EB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// occupancy-grid collision checks (collision_kernels.cuh)
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+struct eb_grid
+{
+  int device = 0;
+  eb::GridView view{};
+  signed char* d_data = nullptr;
+  cudaStream_t stream = nullptr;
+  double* d_a = nullptr;  // staging for the _host calls: poses / x0
+  double* d_b = nullptr;  // twists
+  int* d_out = nullptr;
+  int cap = 0;
+  long long launches = 0;
+};
+
+namespace
+{
+// the checks of the Collision constructor (collision.cpp:46-64) and the radii of
+// CollisionConfig (collision.cpp:130-133)
+eb_status collision_params(const eb_grid* g, const eb_collision* c, eb::CollisionParams* p)
+{
+  if (!g || !c) return fail(EB_ERR_INVALID_ARGUMENT, "grid / collision is NULL");
+  if (c->search_radius < c->boundary_radius)
+    return fail(EB_ERR_INVALID_ARGUMENT, "Search radius must be at least the same size as the boundary radius");
+  if (c->occupied_threshold > 100.0 || c->occupied_threshold < 0.0)
+    return fail(EB_ERR_INVALID_ARGUMENT, "Occupied threshold must be between 0 and 100");
+  p->g = g->view;
+  p->r_bnd = (int)std::floor(c->boundary_radius / g->view.resolution);
+  p->r_col = (int)std::floor((c->boundary_radius + c->obstacle_threshold) / g->view.resolution);
+  p->r_max = (int)std::floor(c->search_radius / g->view.resolution);
+  p->occupied_threshold = c->occupied_threshold;
+  return EB_OK;
+}
+
+eb_status grid_reserve(eb_grid* g, int count)
+{
+  if (count <= g->cap) return EB_OK;
+  cudaFree(g->d_a);
+  cudaFree(g->d_b);
+  cudaFree(g->d_out);
+  g->d_a = g->d_b = nullptr;
+  g->d_out = nullptr;
+  g->cap = 0;
+  EB_CUDA(cudaMalloc(&g->d_a, sizeof(double) * 3 * (size_t)count));
+  EB_CUDA(cudaMalloc(&g->d_b, sizeof(double) * 3 * (size_t)count));
+  EB_CUDA(cudaMalloc(&g->d_out, sizeof(int) * (size_t)count));
+  g->cap = count;
+  return EB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+eb_status eb_grid_create(int device, const signed char* data, unsigned int xsize, unsigned int ysize,
+                         double resolution, double xmin, double ymin, eb_grid** out)
+{
+  if (!out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_grid_create: out is NULL");
+  *out = nullptr;
+  if (!data || xsize == 0 || ysize == 0 || !(resolution > 0.0))
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_grid_create: need data, xsize, ysize >= 1 and resolution > 0");
+  EB_CUDA(cudaSetDevice(device));
+  eb_grid* g = new (std::nothrow) eb_grid();
+  if (!g) return fail(EB_ERR_CUDA, "out of host memory");
+  g->device = device;
+  const size_t cells = (size_t)xsize * ysize;
+  cudaError_t e = cudaMalloc(&g->d_data, cells);
+  if (e == cudaSuccess) e = cudaMemcpy(g->d_data, data, cells, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess)
+  {
+    eb_grid_destroy(g);
+    return fail(EB_ERR_CUDA, std::string("eb_grid_create: ") + cudaGetErrorString(e));
+  }
+  g->view = eb::GridView{ g->d_data, xsize, ysize, resolution, xmin, ymin };
+  *out = g;
+  return EB_OK;
+}
+
+eb_status eb_grid_update(eb_grid* g, const signed char* data)
+{
+  if (!g || !data) return fail(EB_ERR_INVALID_ARGUMENT, "eb_grid_update: NULL argument");
+  EB_CUDA(cudaSetDevice(g->device));
+  EB_CUDA(cudaMemcpyAsync(g->d_data, data, (size_t)g->view.xsize * g->view.ysize, cudaMemcpyHostToDevice, g->stream));
+  EB_CUDA(cudaStreamSynchronize(g->stream));
+  return EB_OK;
+}
+
+void eb_grid_destroy(eb_grid* g)
+{
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaFree(g->d_data);
+  cudaFree(g->d_a);
+  cudaFree(g->d_b);
+  cudaFree(g->d_out);
+  delete g;
+}
+
+eb_status eb_grid_set_stream(eb_grid* g, void* s)
+{
+  if (!g) return fail(EB_ERR_INVALID_ARGUMENT, "grid is NULL");
+  g->stream = static_cast<cudaStream_t>(s);
+  return EB_OK;
+}
+
+long long eb_grid_launch_count(const eb_grid* g) { return g ? g->launches : 0; }
+
+eb_status eb_collision_check_dev(eb_grid* g, const eb_collision* c, const double* poses_dev, int count, int* hit_dev)
+{
+  eb::CollisionParams p{};
+  eb_status st = collision_params(g, c, &p);
+  if (st != EB_OK) return st;
+  if (count < 0 || (count > 0 && (!poses_dev || !hit_dev)))
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_collision_check: bad arguments");
+  if (count == 0) return EB_OK;
+  EB_CUDA(cudaSetDevice(g->device));
+  p.B = count;
+  p.x0 = poses_dev;
+  p.out = hit_dev;
+  eb::collision_check_kernel<<<(count + 127) / 128, 128, 0, g->stream>>>(p);
+  EB_CUDA(cudaGetLastError());
+  g->launches += 1;
+  return EB_OK;
+}
+
+eb_status eb_validate_control_dev(eb_grid* g, const eb_collision* c, const double* x0_dev, const double* u_dev,
+                                  int count, double dt, double horizon, int* valid_dev)
+{
+  eb::CollisionParams p{};
+  eb_status st = collision_params(g, c, &p);
+  if (st != EB_OK) return st;
+  if (count < 0 || (count > 0 && (!x0_dev || !u_dev || !valid_dev)) || dt == 0.0)
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_validate_control: bad arguments");
+  if (count == 0) return EB_OK;
+  EB_CUDA(cudaSetDevice(g->device));
+  p.B = count;
+  p.x0 = x0_dev;
+  p.u = u_dev;
+  p.out = valid_dev;
+  p.dt = dt;
+  p.steps = (int)static_cast<unsigned int>(std::abs(horizon / dt));  // numerics.hpp:316
+  eb::validate_control_kernel<<<(count + 127) / 128, 128, 0, g->stream>>>(p);
+  EB_CUDA(cudaGetLastError());
+  g->launches += 1;
+  return EB_OK;
+}
+
+eb_status eb_collision_check_host(eb_grid* g, const eb_collision* c, const double* poses, int count, int* hit)
+{
+  if (!g) return fail(EB_ERR_INVALID_ARGUMENT, "grid is NULL");
+  if (count > 0 && (!poses || !hit)) return fail(EB_ERR_INVALID_ARGUMENT, "eb_collision_check_host: NULL argument");
+  if (count <= 0) return count == 0 ? EB_OK : fail(EB_ERR_INVALID_ARGUMENT, "count < 0");
+  EB_CUDA(cudaSetDevice(g->device));
+  eb_status st = grid_reserve(g, count);
+  if (st != EB_OK) return st;
+  EB_CUDA(cudaMemcpyAsync(g->d_a, poses, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream));
+  st = eb_collision_check_dev(g, c, g->d_a, count, g->d_out);
+  if (st != EB_OK) return st;
+  EB_CUDA(cudaMemcpyAsync(hit, g->d_out, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, g->stream));
+  EB_CUDA(cudaStreamSynchronize(g->stream));
+  return EB_OK;
+}
+
+eb_status eb_validate_control_host(eb_grid* g, const eb_collision* c, const double* x0, const double* u, int count,
+                                   double dt, double horizon, int* valid)
+{
+  if (!g) return fail(EB_ERR_INVALID_ARGUMENT, "grid is NULL");
+  if (count > 0 && (!x0 || !u || !valid)) return fail(EB_ERR_INVALID_ARGUMENT, "eb_validate_control_host: NULL argument");
+  if (count <= 0) return count == 0 ? EB_OK : fail(EB_ERR_INVALID_ARGUMENT, "count < 0");
+  EB_CUDA(cudaSetDevice(g->device));
+  eb_status st = grid_reserve(g, count);
+  if (st != EB_OK) return st;
+  EB_CUDA(cudaMemcpyAsync(g->d_a, x0, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream));
+  EB_CUDA(cudaMemcpyAsync(g->d_b, u, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream));
+  st = eb_validate_control_dev(g, c, g->d_a, g->d_b, count, dt, horizon, g->d_out);
+  if (st != EB_OK) return st;
+  EB_CUDA(cudaMemcpyAsync(valid, g->d_out, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, g->stream));
+  EB_CUDA(cudaStreamSynchronize(g->stream));
   return EB_OK;
 }
 
