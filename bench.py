@@ -254,11 +254,25 @@ def run_ours(args, wl, rank, world, local_rank):
     side = torch.cuda.Stream(device=dev) if world > 1 else None
     state = {"i": 0, "gather_done": None}
 
+    # N > 1: the gather of the first twists is fused into the solve kernel (P2P stores into
+    # every rank's gathered buffer over NVLink, csrc/peer_gather.cuh); NCCL is only the fallback
+    pg, gather_kind = None, "none (single GPU)"
+    if world > 1:
+        try:
+            from ergodic_exploration_b200.sharding import PeerGather
+            pg = PeerGather(ctl)
+            gather_kind = "fused into the solve kernel: P2P stores over NVLink peer memory + arrival flags"
+        except Exception as exc:  # no peer access between these GPUs
+            pg = None
+            gather_kind = f"NCCL all_gather per step on a side stream (peer mapping failed: {exc})"
+
     def step_dev():
-        """one control() over this rank's instances; for N > 1 the all_gather of
-        step i runs on a side stream and overlaps step i+1's kernel (the ranks
-        own their instances, nothing in the next step depends on the gather);
-        step i+1 does not finish before gather i has."""
+        """one control() over this rank's instances.  Fused gather: the kernel publishes its rows
+        into every rank's gathered buffer (four rotate; reuse is guarded inside the kernel).
+        NCCL fallback: the all_gather of step i runs on a side stream and overlaps step i + 1."""
+        if pg is not None:
+            pg.control(BOUNDS, xd, metric=metd)
+            return
         buf = u0bufs[state["i"] & 1]
         state["i"] += 1
         ctl.control(BOUNDS, xd, u0=buf, metric=metd)
@@ -282,7 +296,9 @@ def run_ours(args, wl, rank, world, local_rank):
         torch.cuda._sleep(int(min(steps, 400) * 150e-6 * 1.9e9))
 
     def drain():
-        if world > 1 and state["gather_done"] is not None:
+        if pg is not None:
+            pg.wait(pg.steps)  # every rank's rows of the last step have arrived here
+        elif world > 1 and state["gather_done"] is not None:
             torch.cuda.current_stream().wait_event(state["gather_done"])
             state["gather_done"] = None
 
@@ -318,6 +334,14 @@ def run_ours(args, wl, rank, world, local_rank):
     ctl.check()
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
 
+    if pg is not None:
+        # the fused gather against a collective: every rank's copy must equal the all_gather of the row blocks
+        mine = pg.gathered()[rank * B:(rank + 1) * B].clone()
+        ref = torch.empty((world * B, 3), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(ref, mine)
+        if not torch.equal(ref, pg.gathered()):
+            raise SystemExit("bench.py: fused peer gather disagrees with NCCL all_gather")
+
     # kernel-only duration for the roofline (single rank / no collective in the pair)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     head_start(args.steps)
@@ -345,6 +369,8 @@ def run_ours(args, wl, rank, world, local_rank):
     e2e_s = time.perf_counter() - e0
     clk = clocks.stop() if rank == 0 else None
 
+    if pg is not None:
+        pg.close()
     if world > 1:
         t = torch.tensor([t_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -385,9 +411,8 @@ def run_ours(args, wl, rank, world, local_rank):
                              "enqueues ahead of the device (spin-kernel head start), so a pair brackets the "
                              "step's device work, not host launch latency",
                    "ck_by_product": "off",
-                   "parallelism": f"instances sharded over {world} GPU(s), one NCCL all_gather of u0 per step on a side "
-                                  f"stream (overlaps the next step's kernel)" if world > 1
-                   else "single GPU"},
+                   "parallelism": f"instances sharded over {world} GPUs, no data-path collective; gather of u0: {gather_kind}"
+                   if world > 1 else "single GPU"},
         "e2e": {"value": world * B * args.steps / e2e_s, "unit": "solves/s",
                 "h2d_bytes_per_step": B * 3 * 8, "d2h_bytes_per_step": B * 3 * 8 + 4,
                 "ms_per_step": e2e_s / args.steps * 1e3,

@@ -117,6 +117,15 @@ SIGNATURES = {
     "eb_basis_spatial_coeff_host": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, _vp, _vp, C.c_longlong, _vp]),
     "eb_target_fill_host": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_longlong, _vp]),
     "eb_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
+    "eb_peer_blob_bytes": (C.c_int, []),
+    "eb_peer_group_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_longlong, C.POINTER(_vp)]),
+    "eb_peer_group_export": (C.c_int, [_vp, _vp]),
+    "eb_peer_group_connect": (C.c_int, [_vp, _vp]),
+    "eb_peer_group_destroy": (None, [_vp]),
+    "eb_control_dev_gather": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp]),
+    "eb_peer_group_wait": (C.c_int, [_vp, _vp, C.c_ulonglong]),
+    "eb_peer_gathered_dev": (_vp, [_vp, C.c_ulonglong]),
+    "eb_peer_group_steps": (C.c_ulonglong, [_vp]),
     "eb_grid_create": (C.c_int, [C.c_int, _vp, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.POINTER(_vp)]),
     "eb_grid_update": (C.c_int, [_vp, _vp]),
     "eb_grid_destroy": (None, [_vp]),

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "collision_kernels.cuh"
+#include "peer_gather.cuh"
 #include "phik_dmma.cuh"
 #include "phik_kernels.cuh"
 #include "solve_kernel.cuh"
@@ -363,6 +364,18 @@ eb_status eb_phik_from_grid_host(int device, const double* phi, int nx, int ny, 
 // ---------------------------------------------------------------------------
 // controller
 // ---------------------------------------------------------------------------
+// arguments of one fused-gather launch (peer_gather.cuh)
+struct PeerLaunch
+{
+  int n_peer = 0;
+  double* u0_peer[eb::kMaxPeers] = {};
+  unsigned long long* flag_peer[eb::kMaxPeers] = {};
+  unsigned long long flag_value = 0;
+  unsigned int* done_counter = nullptr;
+  const unsigned long long* my_flags = nullptr;
+  unsigned long long need = 0;
+};
+
 struct eb_controller
 {
   eb_config cfg{};
@@ -390,6 +403,7 @@ struct eb_controller
   long long launches = 0;
   bool have_pose = false;
   bool keep_ck = true;  // store the c_k by-product of every control() (eb_get_ck)
+  const struct PeerLaunch* peer = nullptr;  // set for the duration of eb_control_dev_gather
 
   // device alias of a page-locked host buffer (nullptr for pageable memory);
   // looked up on every call -- a cached answer could outlive the allocation
@@ -834,6 +848,19 @@ eb_status eb_control_dev(eb_controller* c, double xmin, double xmax, double ymin
   p.metric = metric_dev;
   p.ck = c->keep_ck ? c->d_ck : nullptr;
   p.fault = c->d_fault;
+  if (c->peer)
+  {
+    p.n_peer = c->peer->n_peer;
+    for (int q = 0; q < p.n_peer; q++)
+    {
+      p.u0_peer[q] = c->peer->u0_peer[q];
+      p.flag_peer[q] = c->peer->flag_peer[q];
+    }
+    p.flag_value = c->peer->flag_value;
+    p.done_counter = c->peer->done_counter;
+    p.my_flags = c->peer->my_flags;
+    p.need = c->peer->need;
+  }
   const int rounds = (c->N + 31) / 32;
   cudaError_t e = launch_solve(p, c->cfg.model, rounds, c->stream);
   if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("solve_kernel launch: ") + cudaGetErrorString(e));
@@ -1070,6 +1097,169 @@ eb_status eb_target_fill_host(int device, int ng, const double* mu, const double
   eb::vector_div_kernel<<<blocks, 256>>>(dv.p, G, dt.p);  // target.cpp:87
   EB_CUDA(cudaGetLastError());
   EB_CUDA(cudaMemcpy(phi_vals, dv.p, sizeof(double) * G, cudaMemcpyDeviceToHost));
+  return EB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fused multi-GPU gather over peer memory (peer_gather.cuh)
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+struct eb_peer_group
+{
+  int device = 0, rank = 0, world = 1;
+  long long elems = 0;                          // doubles per rank and step (3 * batch)
+  double* gathered[eb::kPeerBuffers] = {};      // own copies, [world * elems], rotating by step
+  unsigned long long* flags = nullptr;          // own arrival flags, [world]
+  unsigned int* counter = nullptr;
+  double* peer_gathered[eb::kMaxPeers][eb::kPeerBuffers] = {};  // every rank's buffers as seen from here (own: the local pointers)
+  unsigned long long* peer_flags[eb::kMaxPeers] = {};
+  bool connected = false;
+  unsigned long long step = 0;                  // steps launched so far
+};
+
+extern "C" {
+
+int eb_peer_blob_bytes(void) { return (eb::kPeerBuffers + 1) * (int)sizeof(cudaIpcMemHandle_t); }
+
+eb_status eb_peer_group_create(int device, int rank, int world, long long elems_per_rank, eb_peer_group** out)
+{
+  if (!out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_peer_group_create: out is NULL");
+  *out = nullptr;
+  if (world < 1 || world > eb::kMaxPeers || rank < 0 || rank >= world || elems_per_rank < 1)
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_peer_group_create: need 1 <= world <= 8, 0 <= rank < world, elems >= 1");
+  EB_CUDA(cudaSetDevice(device));
+  eb_peer_group* g = new (std::nothrow) eb_peer_group();
+  if (!g) return fail(EB_ERR_CUDA, "out of host memory");
+  g->device = device;
+  g->rank = rank;
+  g->world = world;
+  g->elems = elems_per_rank;
+  const size_t bytes = sizeof(double) * (size_t)world * (size_t)elems_per_rank;
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < eb::kPeerBuffers && e == cudaSuccess; k++)
+  {
+    e = cudaMalloc(&g->gathered[k], bytes);
+    if (e == cudaSuccess) e = cudaMemset(g->gathered[k], 0, bytes);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&g->flags, sizeof(unsigned long long) * eb::kMaxPeers);
+  if (e == cudaSuccess) e = cudaMalloc(&g->counter, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(g->flags, 0, sizeof(unsigned long long) * eb::kMaxPeers);
+  if (e == cudaSuccess) e = cudaMemset(g->counter, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess)
+  {
+    eb_peer_group_destroy(g);
+    return fail(EB_ERR_CUDA, std::string("eb_peer_group_create: ") + cudaGetErrorString(e));
+  }
+  *out = g;
+  return EB_OK;
+}
+
+// blob = IPC handles of {gathered[0..kPeerBuffers), flags}; all_gather the blobs of all ranks (rank order)
+eb_status eb_peer_group_export(eb_peer_group* g, unsigned char* blob)
+{
+  if (!g || !blob) return fail(EB_ERR_INVALID_ARGUMENT, "eb_peer_group_export: NULL argument");
+  EB_CUDA(cudaSetDevice(g->device));
+  cudaIpcMemHandle_t h[eb::kPeerBuffers + 1];
+  for (int k = 0; k < eb::kPeerBuffers; k++) EB_CUDA(cudaIpcGetMemHandle(&h[k], g->gathered[k]));
+  EB_CUDA(cudaIpcGetMemHandle(&h[eb::kPeerBuffers], g->flags));
+  std::memcpy(blob, h, sizeof(h));
+  return EB_OK;
+}
+
+eb_status eb_peer_group_connect(eb_peer_group* g, const unsigned char* blobs)
+{
+  if (!g || (g->world > 1 && !blobs)) return fail(EB_ERR_INVALID_ARGUMENT, "eb_peer_group_connect: NULL argument");
+  EB_CUDA(cudaSetDevice(g->device));
+  for (int r = 0; r < g->world; r++)
+  {
+    if (r == g->rank)
+    {
+      for (int k = 0; k < eb::kPeerBuffers; k++) g->peer_gathered[r][k] = g->gathered[k];
+      g->peer_flags[r] = g->flags;
+      continue;
+    }
+    cudaIpcMemHandle_t h[eb::kPeerBuffers + 1];
+    std::memcpy(h, blobs + (size_t)r * sizeof(h), sizeof(h));
+    void* ptr[eb::kPeerBuffers + 1] = {};
+    for (int k = 0; k <= eb::kPeerBuffers; k++)
+    {
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr[k], h[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return fail(EB_ERR_CUDA, std::string("eb_peer_group_connect: cudaIpcOpenMemHandle (peer access over "
+                                             "NVLink is required): ") + cudaGetErrorString(e));
+    }
+    for (int k = 0; k < eb::kPeerBuffers; k++) g->peer_gathered[r][k] = static_cast<double*>(ptr[k]);
+    g->peer_flags[r] = static_cast<unsigned long long*>(ptr[eb::kPeerBuffers]);
+  }
+  g->connected = true;
+  return EB_OK;
+}
+
+void eb_peer_group_destroy(eb_peer_group* g)
+{
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  if (g->connected)
+    for (int r = 0; r < g->world; r++)
+      if (r != g->rank)
+      {
+        for (int k = 0; k < eb::kPeerBuffers; k++) cudaIpcCloseMemHandle(g->peer_gathered[r][k]);
+        cudaIpcCloseMemHandle(g->peer_flags[r]);
+      }
+  for (int k = 0; k < eb::kPeerBuffers; k++) cudaFree(g->gathered[k]);
+  cudaFree(g->flags);
+  cudaFree(g->counter);
+  delete g;
+}
+
+// device pointer of this rank's copy of the gathered first twists of step `step` (1-based count of
+// eb_control_dev_gather calls): [world][batch][3]
+double* eb_peer_gathered_dev(eb_peer_group* g, unsigned long long step)
+{
+  return (g && step >= 1) ? g->gathered[(step - 1) % eb::kPeerBuffers] : nullptr;
+}
+
+unsigned long long eb_peer_group_steps(const eb_peer_group* g) { return g ? g->step : 0; }
+
+// control() whose first twists land in every rank's gathered buffer (no collective call)
+eb_status eb_control_dev_gather(eb_controller* c, eb_peer_group* g, double xmin, double xmax, double ymin, double ymax,
+                                const double* x_dev, const int* mem_idx_dev, double* metric_dev)
+{
+  if (!c || !g) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather: NULL argument");
+  if (!g->connected) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather: peer group is not connected");
+  if (g->elems != 3LL * c->B) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather: peer group sized for another batch");
+  PeerLaunch pl;
+  const int parity = (int)(g->step % eb::kPeerBuffers);
+  pl.n_peer = g->world;
+  for (int r = 0; r < g->world; r++)
+  {
+    pl.u0_peer[r] = g->peer_gathered[r][parity] + (size_t)g->rank * (size_t)g->elems;
+    pl.flag_peer[r] = g->peer_flags[r] + g->rank;
+  }
+  pl.flag_value = g->step + 1;
+  pl.done_counter = g->counter;
+  pl.my_flags = g->flags;
+  // launching step n + 1 = g->step + 1 into the buffer of step n + 1 - kPeerBuffers: every rank must
+  // have finished step n + 2 - kPeerBuffers (its reads of the older step precede that launch)
+  pl.need = g->step + 2 > (unsigned long long)eb::kPeerBuffers ? g->step + 2 - eb::kPeerBuffers : 0;
+  c->peer = &pl;
+  const eb_status st = eb_control_dev(c, xmin, xmax, ymin, ymax, x_dev, mem_idx_dev, c->d_u0, metric_dev);
+  c->peer = nullptr;
+  if (st == EB_OK) g->step += 1;
+  return st;
+}
+
+// enqueues (on the controller's stream) a wait until every rank's rows of step `step` have arrived here
+eb_status eb_peer_group_wait(eb_peer_group* g, eb_controller* c, unsigned long long step)
+{
+  if (!g || !c) return fail(EB_ERR_INVALID_ARGUMENT, "eb_peer_group_wait: NULL argument");
+  EB_CUDA(cudaSetDevice(g->device));
+  eb::peer_wait_kernel<<<1, 32, 0, c->stream>>>(g->flags, g->world, step);
+  EB_CUDA(cudaGetLastError());
+  c->launches += 1;
   return EB_OK;
 }
 

@@ -37,6 +37,8 @@ constexpr int kModelOmni = 1;
 #define EB_SOLVE_WARPS 4
 #endif
 constexpr int kSolveWarps = EB_SOLVE_WARPS;  // warps (instances in flight) per CTA
+constexpr int kMaxPeers = 8;     // ranks of one NVSwitch box
+constexpr int kPeerBuffers = 4;  // gathered buffers rotating by step (fused gather)
 constexpr int kTabSlots = 16;    // time slots per coefficient chunk (half a round)
 constexpr int kTabStride = 20;   // 16 slots + 4 pad: 20 % 16 == 4 -> conflict-free fragment loads
 
@@ -77,6 +79,15 @@ struct SolveParams
   double* metric;        // [B] or null
   double* ck;            // [B][nb*nb] or null
   int* fault;
+  // fused gather over NVLink peer memory (peer_gather.cuh): every rank's copy of the
+  // gathered first twists, already offset to this rank's row block; 0 = off
+  int n_peer;
+  double* u0_peer[kMaxPeers];
+  unsigned long long* flag_peer[kMaxPeers];  // this rank's slot in every rank's arrival flags
+  unsigned long long flag_value;             // written there once all of this rank's rows have landed
+  unsigned int* done_counter;                // warps of this launch that have published their row
+  const unsigned long long* my_flags;        // this rank's own arrival flags [n_peer] ...
+  unsigned long long need;                   // ... must all have reached this before the buffer is reused
 };
 
 template <int MODEL>
@@ -543,7 +554,39 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
       // first twist: lanes 0..2 store one contiguous 24-byte segment (u0 may live in mapped host memory)
       const double a0 = __shfl_sync(kFull, un[0], 0), a1 = __shfl_sync(kFull, un[1], 0),
                    a2 = __shfl_sync(kFull, un[2], 0);
-      if (lane < 3) p.u0[(size_t)inst * 3 + lane] = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+      const double mine = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+      if (lane < 3) p.u0[(size_t)inst * 3 + lane] = mine;
+      if (p.n_peer > 0)
+      {
+        // The gather IS these stores: the row goes straight into every rank's gathered
+        // buffer over NVLink (P2P stores, no separate collective, nothing to wait for
+        // on this rank).  When the last warp of the launch has published its row, this
+        // rank's arrival flag is raised on every peer (release at system scope).
+        // Buffer reuse: this step's buffer was last written kPeerBuffers steps ago; a rank
+        // reads a step's rows before it launches the next step, so once every rank has
+        // FINISHED step (this - kPeerBuffers + 1) -- p.need, long past in a balanced run --
+        // nobody can still be reading it.  Checked here, at the end of the warp's work.
+        if (lane < p.n_peer)
+          while (*(const volatile unsigned long long*)(p.my_flags + lane) < p.need) __nanosleep(100);
+        __syncwarp();
+        if (lane < 3)
+          for (int q = 0; q < p.n_peer; q++) p.u0_peer[q][(size_t)inst * 3 + lane] = mine;
+        // release at GPU scope into the arrival counter; the last warp's system-scope fence is
+        // cumulative over every row it has thereby observed (PTX memory model), so only that
+        // one warp pays for a system fence
+        __threadfence();
+        __syncwarp();
+        if (lane == 0)
+        {
+          const unsigned int prev = atomicAdd(p.done_counter, 1u);
+          if (prev == (unsigned int)p.B - 1u)
+          {
+            *p.done_counter = 0u;  // ready for the next launch on this stream
+            __threadfence_system();
+            for (int q = 0; q < p.n_peer; q++) *(volatile unsigned long long*)p.flag_peer[q] = p.flag_value;
+          }
+        }
+      }
     }
   }
   EB_PHASE(4);

@@ -9,14 +9,22 @@ The hot path shards by construction:
   * phi_k: the density grid is partitioned by row blocks, every rank contracts
     its rows (eb_phik_execute_raw_dev) and ONE all_reduce(sum) of the 32x32 raw
     block (which includes sum(Phi) at [0,0]) finishes the job.
+  * PeerGather replaces that per-step all_gather by the fused gather of
+    csrc/peer_gather.cuh: every rank maps the others' gathered buffers once
+    (CUDA IPC, NVLink peer memory) and the solve kernel itself stores its rows
+    into all of them -- no collective call inside the step.
 Nothing here computes; it only decides who owns what and moves results.
 """
 from __future__ import annotations
 
-from typing import List, Tuple
+import ctypes as C
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+from . import capi
+from .capi import check
 
 
 def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
@@ -89,3 +97,96 @@ class ShardedErgodicControl:
         if not gather or self.world == 1:
             return u0
         return all_gather_rows(u0, self.total, self.group)
+
+
+class _DevView:
+    """zero-copy torch view of device memory owned by the C library"""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerGather:
+    """Fused gather of the first twists over NVLink peer memory for one rank's
+    ErgodicControl (include/ergodic_b200.h, eb_peer_group_*).  Collective at
+    construction (the ranks exchange CUDA IPC handles with one all_gather of a
+    few hundred bytes); afterwards ``control()`` launches the solve kernel, which
+    writes this rank's rows into every rank's gathered buffer by itself."""
+
+    def __init__(self, ctl, group=None):
+        self._lib = capi.load()
+        self.ctl, self.group = ctl, group
+        multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else 0
+        h = C.c_void_p()
+        check(self._lib.eb_peer_group_create(ctl.device, self.rank, self.world, 3 * ctl.batch, C.byref(h)))
+        self._h = h
+        nbytes = self._lib.eb_peer_blob_bytes()
+        blob = (C.c_ubyte * nbytes)()
+        check(self._lib.eb_peer_group_export(h, blob))
+        if multi:
+            dev = torch.device("cuda", ctl.device)
+            mine = torch.tensor(list(bytes(blob)), dtype=torch.uint8, device=dev)
+            allb = torch.empty(self.world * nbytes, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allb, mine, group=group)
+            raw = bytes(allb.cpu().numpy().tobytes())
+            buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+            st = self._lib.eb_peer_group_connect(h, buf)
+            # every rank has mapped every buffer before the first store -- or all give up together
+            ok = torch.tensor([1 if st == capi.EB_OK else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                msg = self._lib.eb_last_error().decode(errors="replace") if st != capi.EB_OK else "failed on another rank"
+                self._lib.eb_peer_group_destroy(h)
+                self._h = None
+                raise RuntimeError(f"peer mapping: {msg}")
+        else:
+            check(self._lib.eb_peer_group_connect(h, None))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            if dist.is_initialized() and self.world > 1:
+                torch.cuda.synchronize(self.ctl.device)
+                dist.barrier(group=self.group)  # nobody is still storing into a buffer about to be freed
+            self._lib.eb_peer_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.eb_peer_group_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def steps(self) -> int:
+        return int(self._lib.eb_peer_group_steps(self._h))
+
+    def control(self, grid, x: torch.Tensor, mem_idx: Optional[torch.Tensor] = None,
+                metric: Optional[torch.Tensor] = None) -> int:
+        """one control() step of this rank's instances; returns the step number (1-based)
+        whose gathered rows ``gathered(step)`` will hold once ``wait(step)`` has passed"""
+        b = grid.as_tuple() if hasattr(grid, "as_tuple") else tuple(float(v) for v in grid)
+        self.ctl._sync_stream()
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == 3 * self.ctl.batch
+        idx_p = C.c_void_p(mem_idx.data_ptr()) if mem_idx is not None else None
+        met_p = C.c_void_p(metric.data_ptr()) if metric is not None else None
+        st = self._lib.eb_control_dev_gather(self.ctl._h, self._h, *b, C.c_void_p(x.data_ptr()), idx_p, met_p)
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(self._lib.eb_last_error().decode())
+        check(st)
+        return self.steps
+
+    def wait(self, step: Optional[int] = None) -> None:
+        """enqueue (on the current stream) a wait until every rank's rows of ``step`` are here"""
+        self.ctl._sync_stream()
+        check(self._lib.eb_peer_group_wait(self._h, self.ctl._h, int(self.steps if step is None else step)))
+
+    def gathered(self, step: Optional[int] = None) -> torch.Tensor:
+        """this rank's copy of all ranks' first twists of ``step``: (world * batch, 3), zero-copy"""
+        step = self.steps if step is None else step
+        ptr = self._lib.eb_peer_gathered_dev(self._h, int(step))
+        return torch.as_tensor(_DevView(ptr, (self.world * self.ctl.batch, 3)), device=torch.device("cuda", self.ctl.device))

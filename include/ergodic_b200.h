@@ -214,6 +214,31 @@ eb_status eb_basis_spatial_coeff_host(int device, double lx, double ly, int nb, 
 eb_status eb_target_fill_host(int device, int ng, const double *mu, const double *sigma,
                               const double *trans, const double *phi_grid, long long G, double *phi_vals);
 
+/* ---- fused multi-GPU gather of the first twists --------
+ * One process per GPU; the instances are block-partitioned and the only exchange of
+ * a control() step is the gather of u0.  Instead of a collective call per step, every
+ * rank maps every other rank's gathered buffer once (CUDA IPC over NVLink / NVSwitch
+ * peer memory) and the solve kernel stores its rows into all of them directly.
+ *   create -> export blob -> exchange the blobs of all ranks (e.g. one all_gather of
+ *   eb_peer_blob_bytes() bytes at start-up) -> connect -> eb_control_dev_gather per step.
+ * eb_peer_group_wait enqueues a wait until all ranks' rows of a step have arrived here;
+ * eb_peer_gathered_dev is this rank's copy, [world][batch][3] doubles.  Four buffers rotate by
+ * step: read a step's rows (after its wait) before launching the next step on the same stream,
+ * and the kernel itself holds back its stores until every rank is past the reads of the step
+ * whose buffer it is about to reuse -- no per-step wait is needed between launches. */
+typedef struct eb_peer_group eb_peer_group;
+int eb_peer_blob_bytes(void);
+eb_status eb_peer_group_create(int device, int rank, int world, long long elems_per_rank /* 3 * batch */,
+                               eb_peer_group **out);
+eb_status eb_peer_group_export(eb_peer_group *g, unsigned char *blob);
+eb_status eb_peer_group_connect(eb_peer_group *g, const unsigned char *blobs /* world blobs, rank order */);
+void eb_peer_group_destroy(eb_peer_group *g);
+eb_status eb_control_dev_gather(eb_controller *c, eb_peer_group *g, double xmin, double xmax, double ymin,
+                                double ymax, const double *x_dev, const int *mem_idx_dev, double *metric_dev);
+eb_status eb_peer_group_wait(eb_peer_group *g, eb_controller *c, unsigned long long step);
+double *eb_peer_gathered_dev(eb_peer_group *g, unsigned long long step);
+unsigned long long eb_peer_group_steps(const eb_peer_group *g);
+
 /* ---- occupancy-grid collision checks ----------------
  * Batched Collision::collisionCheck (collision.cpp:126-143) and validate_control
  * (numerics.hpp:312-330) -- the call the exploration loop makes on the twist control()

@@ -13,8 +13,10 @@
 #include <cstring>
 #include <iostream>
 #include <stdexcept>
+#include <vector>
 
 #include <ergodic_exploration_b200/ergodic_control.hpp>
+#include <ergodic_exploration_b200/collision.hpp>
 
 using namespace ergodic_exploration;
 
@@ -32,6 +34,26 @@ struct MyGrid
   double xmax() const { return x1; }
   double ymin() const { return y0; }
   double ymax() const { return y1; }
+};
+
+// a map with the reference GridMap's getters (grid.hpp:201-255): a wall and two pillars
+struct MyMap
+{
+  unsigned int nx = 120, ny = 90;
+  std::vector<int8_t> cells = std::vector<int8_t>(size_t(120) * 90, 0);
+  MyMap()
+  {
+    for (unsigned int j = 20; j < 100; j++) cells[40 * nx + j] = 100;
+    cells[10 * nx + 10] = 100;
+    cells[70 * nx + 60] = 77;
+    cells[5 * nx + 100] = -1;
+  }
+  const std::vector<int8_t>& gridData() const { return cells; }
+  unsigned int xsize() const { return nx; }
+  unsigned int ysize() const { return ny; }
+  double resolution() const { return 0.05; }
+  double xmin() const { return -1.0; }
+  double ymin() const { return 0.5; }
 };
 
 #define REQUIRE(cond)                                                     \
@@ -194,6 +216,42 @@ static int run_gpu(const ModelT& model, const mat& Rinv, const vec& umin, const 
   print_vec("xb", xb.memptr(), 9);
   print_vec("ub", ub3.memptr(), 9);
   print_vec("metric", metric.memptr(), 3);
+  // collision checks of the tick that follows control() (exploration.hpp:238)
+  {
+    const MyMap map;
+    const b200::DeviceGrid dgrid(map);
+    const b200::Collision col(0.2, 1.0, 0.05, 0.65);
+    bool threw = false;
+    try
+    {
+      b200::Collision bad(0.5, 0.2, 0.0, 0.5);
+    }
+    catch (const std::invalid_argument&)
+    {
+      threw = true;
+    }
+    REQUIRE(threw);
+    const int B = 24;
+    mat p0(3, B), tw(3, B);
+    for (int i = 0; i < B; i++)
+    {
+      p0(0, i) = -0.8 + 0.23 * i;
+      p0(1, i) = 0.7 + 0.17 * i;
+      p0(2, i) = -3.0 + 0.25 * i;
+      tw(0, i) = 0.9 - 0.07 * i;
+      tw(1, i) = -0.5 + 0.04 * i;
+      tw(2, i) = (i % 4 == 0) ? 0.0 : -1.5 + 0.13 * i;
+    }
+    const std::vector<int> hit = col.collisionCheck(dgrid, p0);
+    const std::vector<int> valid = b200::validate_control(col, dgrid, p0, tw, 0.1, 1.0);
+    REQUIRE(col.collisionCheck(dgrid, vec(p0.col(3))) == (hit[3] != 0));
+    REQUIRE(b200::validate_control(col, dgrid, vec(p0.col(5)), vec(tw.col(5)), 0.1, 1.0) == (valid[5] != 0));
+    print_vec("cpose", p0.memptr(), p0.n_elem);
+    print_vec("ctwist", tw.memptr(), tw.n_elem);
+    std::vector<double> hd(hit.begin(), hit.end()), vd(valid.begin(), valid.end());
+    print_vec("chit", hd.data(), hd.size());
+    print_vec("cvalid", vd.data(), vd.size());
+  }
   std::printf("OK\n");
   return 0;
 }

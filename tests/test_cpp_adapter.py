@@ -82,3 +82,13 @@ def test_adapter_closed_loop_matches_oracle(demo, model):
         ob = make_oracle(model, buffer_size=1000)
         assert_abs_rel_close(rec["ub"][0].reshape(3, 3)[i], ob.control(BOUNDS_10, xb[i]), f"batched u0[{i}]")
         assert_abs_rel_close(rec["metric"][0][i], ob.last()["metric"], f"batched metric[{i}]")
+    # collision checks (include/ergodic_exploration_b200/collision.hpp): the demo's map, rebuilt here
+    data = np.zeros((90, 120), dtype=np.int8)
+    data[40, 20:100] = 100
+    data[10, 10], data[70, 60], data[5, 100] = 100, 77, -1
+    col = (0.2, 1.0, 0.05, 0.65)
+    poses, twists = rec["cpose"][0].reshape(-1, 3), rec["ctwist"][0].reshape(-1, 3)
+    np.testing.assert_array_equal(rec["chit"][0].astype(int), Oracle.collision_check(data, 0.05, -1.0, 0.5, col, poses))
+    np.testing.assert_array_equal(rec["cvalid"][0].astype(int),
+                                  Oracle.validate_control(data, 0.05, -1.0, 0.5, col, poses, twists, 0.1, 1.0))
+    assert 0 < rec["cvalid"][0].sum() < len(poses)

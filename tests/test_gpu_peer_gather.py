@@ -1,0 +1,86 @@
+"""-m gpu: the fused gather of the first twists (csrc/peer_gather.cuh).  On one GPU the
+peer group has a single member (the kernel stores into its own gathered buffer and raises
+its own flag); with two or more GPUs a two-process run checks the rows that arrive over
+NVLink against an NCCL all_gather."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import BOUNDS_10, MODEL_OMNI, make_gpu, plant, random_states, warm_ut
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_single_rank_group_matches_plain_control():
+    import torch
+
+    from ergodic_exploration_b200.sharding import PeerGather
+
+    rng = np.random.default_rng(61)
+    B = 200
+    ut = warm_ut(rng, B, 50, MODEL_OMNI)
+    a, b = make_gpu(MODEL_OMNI, B), make_gpu(MODEL_OMNI, B)
+    a.set_ut(ut)
+    b.set_ut(ut)
+    pg = PeerGather(a)
+    x = random_states(rng, B)
+    for step in range(1, 5):
+        xd = torch.from_numpy(x).cuda()
+        md = torch.empty(B, dtype=torch.float64, device="cuda")
+        assert pg.control(BOUNDS_10, xd, metric=md) == step
+        pg.wait(step)
+        got = pg.gathered(step).cpu().numpy()
+        mb = np.empty(B)
+        want = b.control(BOUNDS_10, x, metric=mb)
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(md.cpu().numpy(), mb)
+        x = plant(x, want)
+    np.testing.assert_array_equal(a.get_ut(), b.get_ut())
+    pg.close()
+
+
+WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from helpers import BOUNDS_10, MODEL_OMNI, make_gpu, random_states, warm_ut
+from ergodic_exploration_b200.sharding import PeerGather
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+B = 512
+rng = np.random.default_rng(100 + rank)
+ctl = make_gpu(MODEL_OMNI, B, device=rank)
+ctl.set_ut(warm_ut(rng, B, 50, MODEL_OMNI))
+pg = PeerGather(ctl)
+x = torch.from_numpy(random_states(rng, B)).cuda()
+for step in range(1, 12):
+    pg.control(BOUNDS_10, x)
+    pg.wait(step)
+    torch.cuda.synchronize()
+    g = pg.gathered(step)
+    ref = torch.empty_like(g)
+    dist.all_gather_into_tensor(ref, g[rank * B:(rank + 1) * B].clone())
+    assert torch.equal(ref, g), f"rank {rank} step {step}: gathered rows differ from all_gather"
+    assert float(g.abs().sum()) > 0
+pg.close()
+dist.destroy_process_group()
+print("PEER_OK", rank)
+"""
+
+
+def test_two_ranks_over_nvlink(tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.count("PEER_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
