@@ -562,14 +562,29 @@ def run_phik(args, rank, world, local_rank):
     }
     if e2e:
         line["e2e"] = e2e
+    if world == 1:
+        # CPU beside it: the reference's spatialCoeff arithmetic (2K cosines per cell; its K x G temporary would
+        # be 550 TB at this size) as streamed by the C restatement, on a bounded sub-grid, one core
+        from oracle import pyoracle
+        from oracle.pyoracle import Oracle
+
+        pyoracle.build()
+        sub = 384
+        phis = phi[:sub, :sub].cpu().numpy()
+        t0 = time.perf_counter()
+        Oracle.phik_from_grid(phis, res, (sub - 1) * res, (sub - 1) * res, nb)
+        dt_cpu = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sub * sub * nb * nb / dt_cpu, "unit": "cell*bases/s", "cores": 1, "kind": "port",
+                                "sample": f"{sub}x{sub} corner of the grid, 32x32 basis, Basis::spatialCoeff arithmetic "
+                                          f"(basis.cpp:122-133) streamed by oracle/ergodic_oracle.c, single thread"}
     print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3"])
     args = ap.parse_args()

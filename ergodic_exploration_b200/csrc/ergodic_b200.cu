@@ -434,14 +434,17 @@ namespace
 template <int MODEL, int NB>
 cudaError_t launch_solve_t(const eb::SolveParams& p, int rounds, cudaStream_t s)
 {
-  const size_t smem = eb::solve_smem_bytes(NB, eb::SolveCfg<NB>::kFields, rounds);
-  static size_t configured = 0;  // per instantiation
-  if (smem > configured)
+  const size_t smem = eb::solve_smem_bytes(eb::SolveCfg<NB>::kTabDoubles, eb::SolveCfg<NB>::kFields, rounds);
+  // the attribute is per device: remember what has been set, per instantiation and device
+  static size_t configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > configured[dev & 63])
   {
     cudaError_t e =
         cudaFuncSetAttribute(eb::solve_kernel<MODEL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured[dev & 63] = smem;
   }
   const int grid = (p.B + eb::kSolveWarps - 1) / eb::kSolveWarps;
   eb::solve_kernel<MODEL, NB><<<grid, eb::kSolveWarps * 32, smem, s>>>(p);

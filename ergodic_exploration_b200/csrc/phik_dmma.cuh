@@ -427,13 +427,15 @@ inline int phik_dmma_launch_t(const double* phi, int nx, int ny, const double* c
   const int row_blocks = (ny + kPdRows - 1) / kPdRows;
   p.total = (long long)row_blocks * p.nchunks;
   const int grid = (int)std::min<long long>(p.total, max_parts);
-  static bool configured = false;  // per instantiation
-  if (!configured)
+  static bool configured[64] = {};  // per instantiation and device (the attribute is per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63])
   {
     if (cudaFuncSetAttribute(phik_dmma_kernel<FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes) !=
         cudaSuccess)
       return -1;
-    configured = true;
+    configured[dev & 63] = true;
   }
   phik_dmma_kernel<FOLD><<<grid, kPdThreads, G::kSmemBytes, stream>>>(p);
   if (cudaGetLastError() != cudaSuccess) return -1;

@@ -40,6 +40,7 @@ constexpr int kSolveWarps = EB_SOLVE_WARPS;  // warps (instances in flight) per 
 constexpr int kMaxPeers = 8;     // ranks of one NVSwitch box
 constexpr int kPeerBuffers = 4;  // gathered buffers rotating by step (fused gather)
 constexpr int kTabSlots = 16;    // time slots per coefficient chunk (half a round)
+constexpr int kGradPitch = 12;   // gradient tables: 8 slots + 4 pad, 12 % 16 -> conflict-free fragment loads
 constexpr int kTabStride = 20;   // 16 slots + 4 pad: 20 % 16 == 4 -> conflict-free fragment loads
 
 #ifdef EB_PHASE_TIMING
@@ -225,6 +226,9 @@ __device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, const int
 //  * kBlock: the gradient's kx range is walked in blocks of kBlock orders so that
 //    only 2 kBlock doubles of cos / sin rows are live in registers.
 //  * kMinBlocks: resident CTAs per SM the register allocation is tuned for.
+#ifndef EB_DMMA_GRAD
+#define EB_DMMA_GRAD 1
+#endif
 #ifndef EB_KB_16
 #define EB_KB_16 8
 #endif
@@ -235,25 +239,32 @@ __device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, const int
 #define EB_MINB_10 7
 #endif
 #ifndef EB_MINB_16
-#define EB_MINB_16 7
+#define EB_MINB_16 6
 #endif
 #ifndef EB_MINB_20
-#define EB_MINB_20 3
+#define EB_MINB_20 4
 #endif
 template <int NB>
 struct SolveCfg
 {
   static constexpr bool kRecompute = NB >= 16;
   static constexpr int kFields = kRecompute ? 4 : 8;
+  // gradient on the FP64 tensor cores (see "DMMA gradient" in solve_kernel): pays when the
+  // 8-row / 4-order tile padding is small, i.e. not for nb <= 12; nb = 32 would need 128
+  // registers of S fragments
+  static constexpr bool kDmmaGrad = EB_DMMA_GRAD && (NB == 16 || NB == 20 || NB == 24);
+  // per-warp table region: the two c_k tables (pitch 20, 16 slots) or the four gradient
+  // tables (pitch 12, 8 slots), whichever is larger; S (NB x NB) aliases it
+  static constexpr int kTabDoubles = kDmmaGrad ? 4 * NB * kGradPitch : 2 * NB * kTabStride;
   static constexpr int kBlock = NB <= 12 ? NB : (NB == 20 ? EB_KB_20 : NB == 16 ? EB_KB_16 : 8);
   static constexpr int kMinBlocks =
       (NB <= 10 ? EB_MINB_10 : NB <= 12 ? 6 : NB <= 16 ? EB_MINB_16 : NB <= 24 ? EB_MINB_20 : 4) * 4 / kSolveWarps;
   static_assert(NB % kBlock == 0, "kx blocks must tile NB");
 };
 
-inline size_t solve_smem_bytes(int NB, int fields, int rounds)
+inline size_t solve_smem_bytes(int tab_doubles, int fields, int rounds)
 {
-  return sizeof(double) * kSolveWarps * (size_t)(2 * NB * kTabStride + fields * 32 * rounds);
+  return sizeof(double) * kSolveWarps * (size_t)(tab_doubles + fields * 32 * rounds);
 }
 
 template <int MODEL, int NB>
@@ -273,8 +284,8 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
   EB_PHASE(0);
 
   // per-warp shared memory: the two cosine tables, then the per-step records
-  double* tabx = smem + warp * (2 * NB * kTabStride + Cfg::kFields * npad);
-  double* rec = tabx + 2 * NB * kTabStride;
+  double* tabx = smem + warp * (Cfg::kTabDoubles + Cfg::kFields * npad);
+  double* rec = tabx + Cfg::kTabDoubles;
   double* Ssm = tabx;  // S (NB x NB) aliases the two tables (2*NB*20 doubles) once c_k is complete
 
   double acc[TILES][TILES][2];
@@ -404,6 +415,32 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
   // ---- per round, last round first: gradient of the ergodic metric, one time
   //      step per lane (:419-436), then the backward co-state pass and the
   //      control update of the same 32 steps (:277, :439-451) -------------------
+  // DMMA gradient (Cfg::kDmmaGrad).  R1 = (S diag(a_kx)) SX and R2 = (diag(b_ky) S) CX for the
+  // 8 time steps of a tile, SX[kx][t] = sin(kx a x_t), CX[kx][t] = cos(kx a x_t), are
+  // products of an nb x nb matrix with an nb x 8 table: S sits in registers as A fragments
+  // (folded with a_kx / b_ky once per instance), the tables are built per tile by the whole
+  // warp -- lane (axis, cos | sin, slot) runs one even/odd Chebyshev-type recurrence -- and
+  // e_x(t) = -w sum_ky cos(ky b y_t) R1[ky][t], e_y(t) = -w sum_ky sin(ky b y_t) R2[ky][t] are a
+  // fragment-wise product with the y tables and a recursive-halving reduction over the 8
+  // row lanes.  Tiles are 8 steps wide, so N = 50 costs 7 tiles instead of two full rounds.
+  constexpr int GKS = (NB + 3) / 4;  // k-steps over kx
+  double SA[Cfg::kDmmaGrad ? TILES : 1][Cfg::kDmmaGrad ? GKS : 1], SB[Cfg::kDmmaGrad ? TILES : 1][Cfg::kDmmaGrad ? GKS : 1];
+  if constexpr (Cfg::kDmmaGrad)
+  {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < TILES; mi++)
+#pragma unroll
+      for (int ks = 0; ks < GKS; ks++)
+      {
+        const int ky = 8 * mi + g, kx = 4 * ks + q;
+        const double sv = (ky < NB && kx < NB) ? Ssm[ky * NB + kx] : 0.0;
+        SA[mi][ks] = sv * ((double)kx * p.ax);
+        SB[mi][ks] = sv * ((double)ky * p.by);
+      }
+    __syncwarp();  // S has been read: the table region is free for the gradient tables
+  }
+
   double r0c = 0.0, r1c = 0.0, r2c = 0.0;  // rho(T) = 0 (:203)
   for (int r = rounds - 1; r >= 0; r--)
   {
@@ -425,6 +462,115 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
       sb = rec[7 * npad + i];
     }
     double ex = 0.0, ey = 0.0;
+    if constexpr (Cfg::kDmmaGrad)
+    {
+      const int g = lane >> 2, q = lane & 3;
+      const int axis = lane >> 4, chain = (lane >> 3) & 1, slot = lane & 7;
+      double* const gt = tabx;  // [axis][chain][k][12]: cos(kx a x) | sin(kx a x) | cos(ky b y) | sin(ky b y)
+      double* const mytab = gt + (axis * 2 + chain) * (NB * kGradPitch) + slot;
+      const double* const txc = gt;
+      const double* const txs = gt + NB * kGradPitch;
+      const double* const tyc = gt + 2 * NB * kGradPitch;
+      const double* const tys = gt + 3 * NB * kGradPitch;
+      // e_x / e_y of the round's 32 steps are handed to the time-step lanes through the pad
+      // slots (8..11) of rows 0..7 of the first two tables
+      auto stage = [&](int which, int t) { return gt + which * (NB * kGradPitch) + (t >> 2) * kGradPitch + 8 + (t & 3); };
+      const int left = p.N - r * 32;  // valid steps in this round (warp-uniform)
+      const int ntiles = min(4, (left + 7) >> 3);
+      for (int nj = 0; nj < ntiles; nj++)
+      {
+        const int src = 8 * nj + slot;
+        const double xc = __shfl_sync(kFull, ca, src), xs = __shfl_sync(kFull, sa, src);
+        const double yc = __shfl_sync(kFull, cb, src), ys = __shfl_sync(kFull, sb, src);
+        const bool ok = __shfl_sync(kFull, (int)valid, src) != 0;
+        const double c = axis ? yc : xc, sn = axis ? ys : xs;
+        // even / odd orders of cos(k t) (chain 0) or sin(k t) (chain 1): v_{k+2} = (4c^2 - 2) v_k - v_{k-2}
+        const double m = fma(4.0 * c, c, -2.0);
+        double em, ek, om, ok1;
+        if (chain == 0)
+        {
+          em = fma(2.0 * c, c, -1.0);  // cos(-2t)
+          ek = 1.0;
+          om = c;  // cos(-t)
+          ok1 = c;
+        }
+        else
+        {
+          em = -2.0 * sn * c;  // sin(-2t)
+          ek = 0.0;
+          om = -sn;  // sin(-t)
+          ok1 = sn;
+        }
+        if (!ok) em = ek = om = ok1 = 0.0;
+        __syncwarp();  // the previous tile's fragment / staging traffic is done
+#pragma unroll
+        for (int k = 0; k < NB; k += 2)
+        {
+          mytab[k * kGradPitch] = ek;
+          mytab[(k + 1) * kGradPitch] = ok1;
+          const double en = fma(m, ek, -em), on = fma(m, ok1, -om);
+          em = ek;
+          ek = en;
+          om = ok1;
+          ok1 = on;
+        }
+        __syncwarp();
+        double R1[TILES][2], R2[TILES][2];
+#pragma unroll
+        for (int mi = 0; mi < TILES; mi++) R1[mi][0] = R1[mi][1] = R2[mi][0] = R2[mi][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < GKS; ks++)
+        {
+          const int kx = 4 * ks + q;
+          const bool in = (GKS * 4 == NB) || (kx < NB);
+          const double bs = in ? txs[kx * kGradPitch + g] : 0.0;
+          const double bc = in ? txc[kx * kGradPitch + g] : 0.0;
+#pragma unroll
+          for (int mi = 0; mi < TILES; mi++)
+          {
+            dmma884(R1[mi][0], R1[mi][1], SA[mi][ks], bs);
+            dmma884(R2[mi][0], R2[mi][1], SB[mi][ks], bc);
+          }
+        }
+        // lane (g, q) holds R[ky = 8 mi + g][slot 2q, 2q + 1]: weight with the y tables
+        double v0 = 0.0, v1 = 0.0, w0 = 0.0, w1 = 0.0;  // e_x, e_y partial sums for slots 2q, 2q + 1
+#pragma unroll
+        for (int mi = 0; mi < TILES; mi++)
+        {
+          const int ky = 8 * mi + g;
+          if ((TILES * 8 == NB) || (ky < NB))
+          {
+            const double2 cy2 = *reinterpret_cast<const double2*>(tyc + ky * kGradPitch + 2 * q);
+            const double2 sy2 = *reinterpret_cast<const double2*>(tys + ky * kGradPitch + 2 * q);
+            v0 = fma(cy2.x, R1[mi][0], v0);
+            v1 = fma(cy2.y, R1[mi][1], v1);
+            w0 = fma(sy2.x, R2[mi][0], w0);
+            w1 = fma(sy2.y, R2[mi][1], w1);
+          }
+        }
+        // sum over the 8 row lanes g (lane = 4 g + q) by recursive halving:
+        //   xor 16: lanes g < 4 keep e_x, g >= 4 keep e_y;  xor 8: keep slot 2q (g & 2 == 0) or 2q + 1;  xor 4: full
+        {
+          const bool hi = (g & 4) != 0;
+          const double s0 = hi ? v0 : w0, s1 = hi ? v1 : w1;  // what the partner keeps
+          double k0 = hi ? w0 : v0, k1 = hi ? w1 : v1;
+          k0 += __shfl_xor_sync(kFull, s0, 16);
+          k1 += __shfl_xor_sync(kFull, s1, 16);
+          const bool odd = (g & 2) != 0;
+          double kk = odd ? k1 : k0;
+          kk += __shfl_xor_sync(kFull, odd ? k0 : k1, 8);
+          kk += __shfl_xor_sync(kFull, kk, 4);
+          if ((g & 1) == 0) *stage(hi ? 1 : 0, 8 * nj + 2 * q + (odd ? 1 : 0)) = kk;
+        }
+      }
+      __syncwarp();
+      if (lane < 8 * ntiles)
+      {
+        ex = *stage(0, lane);
+        ey = *stage(1, lane);
+      }
+    }
+    else
     {
       // (cos, sin)((k-1) a x), (cos, sin)(k a x) started at k = 0, carried across the kx blocks
       double xcm = ca, xck = 1.0, xsm = -sa, xsk = 0.0;
