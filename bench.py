@@ -580,19 +580,162 @@ def run_phik(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_avoid(args, rank, world, local_rank):
+    """widened rows: the collision side of the tick that follows control().
+    collide: validate_control of one twist per robot; dwa: DynamicWindow::control (3 x 8 x 5 window,
+    2 s rollouts) per robot.  One shared 4000 x 4000 map (16 MB int8, L2-resident), explore_omni.yaml
+    radii and limits, 2^18 robots per GPU; the robots are block-partitioned over the ranks with no exchange."""
+    import torch
+    import torch.distributed as dist
+
+    import ergodic_exploration_b200 as eb
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dwa_mode = args.workload == "dwa"
+    rng = np.random.default_rng(0xE16C0D1C + 7 + rank)
+    n, res, B = 4000, 0.05, 1 << 18
+    mrng = np.random.default_rng(0xE16C0D1C + 8)  # the same map on every rank
+    data = np.zeros((n, n), dtype=np.int8)
+    data[mrng.random((n, n)) < 0.002] = 100
+    data[mrng.random((n, n)) < 0.01] = -1
+    colp = (0.7, 1.0, 0.2, 0.8)  # explore_omni.yaml:35-38
+    grid = eb.GridMap(-100.0, 100.0, -100.0, 100.0, res, data, device=local_rank)
+    col = eb.Collision(*colp)
+    x0 = np.column_stack([rng.uniform(-98, 98, B), rng.uniform(-98, 98, B), rng.uniform(-np.pi, np.pi, B)])
+    u = np.column_stack([rng.uniform(-1, 1, B), rng.uniform(-1, 1, B), rng.uniform(-2, 2, B)])
+    xd, ud = torch.from_numpy(x0).to(dev), torch.from_numpy(u).to(dev)
+    dwa_cfg = (0.1, 2.0, 0.2, 2.5, 2.5, 1.0, 1.0, -1.0, 1.0, -1.0, 2.0, -2.0)  # explore_omni.yaml:15-28,65-70
+    dwa = eb.DynamicWindow(col, *dwa_cfg, 3, 8, 5)
+    vref = torch.zeros_like(ud)
+
+    def step():
+        if dwa_mode:
+            return dwa.control(grid, xd, ud, vref=vref)[0]
+        return eb.validate_control(col, grid, xd, ud, 0.1, 0.5)
+
+    def step_host(xh, uh):
+        if dwa_mode:
+            return dwa.control(grid, xh, uh, vref=np.zeros_like(uh))[0]
+        return eb.validate_control(col, grid, xh, uh, 0.1, 0.5)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(3, args.warmup)):
+        out = step()
+    torch.cuda.synchronize()
+    free_frac = float(out.float().mean())
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = grid.launch_count()
+    steps = min(args.steps, 100)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.zero_()  # the map and the poses leave L2 between steps
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = grid.launch_count() - l0
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    # end to end: host poses / twists in, flags out
+    xh, uh = x0.copy(), u.copy()
+    step_host(xh, uh)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        step_host(xh, uh)
+    e2e_s = (time.perf_counter() - t0) / reps
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = t.tolist()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    # algorithmic probes of one full (collision-free) check: the reference's circle walk, pruned radii
+    def circle_cells(r):
+        x, y, err, cnt = -r, 0, 2 - 2 * r, 0
+        while x < 0:
+            cnt += 4
+            rr = err
+            if rr <= y:
+                y += 1
+                err += 2 * y + 1
+            if rr > x or err > y:
+                x += 1
+                err += 2 * x + 1
+        return cnt
+    r_bnd, r_col, r_max = int(colp[0] / res), int((colp[0] + colp[2]) / res), int(colp[1] / res)
+    probes_pose = sum(circle_cells(r) for r in range(r_bnd, min(r_max, r_col) + 1))
+    probes_ref = sum(circle_cells(r) for r in range(r_bnd, r_max + 1))
+    rollouts = 120 if dwa_mode else 1
+    nsteps = 20 if dwa_mode else 5
+    unit = "DWA decisions/s" if dwa_mode else "validated twists/s"
+    line = {
+        "metric": ("DynamicWindow::control decisions/sec (batched)" if dwa_mode else "validate_control twists/sec (batched)"),
+        "value": world * B / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8/f64",
+        "data": "synthetic",
+        "config": {"workload": ("DynamicWindow 3x8x5 window, 2 s rollouts" if dwa_mode else "validate_control, 0.5 s rollout")
+                   + f", {B} robots per GPU on one 4000x4000 map @ 0.05 m, explore_omni.yaml radii",
+                   "collision_free_fraction": free_frac, "l2": "flushed between timed steps",
+                   "parallelism": f"robots block-partitioned over {world} GPU(s), no exchange"},
+        "e2e": {"value": world * B / e2e_s, "unit": unit, "h2d_bytes_per_step": 2 * B * 24,
+                "d2h_bytes_per_step": B * (4 + (24 if dwa_mode else 0)), "ms_per_step": e2e_s * 1e3,
+                "path": "host poses + twists -> H2D -> kernel -> D2H flags" + (" + twists" if dwa_mode else "")},
+        "gpu_launches": int(launches), "clocks": clk,
+        "roofline": {"kernel": "dwa_control_kernel" if dwa_mode else "validate_control_kernel",
+                     "bound": "gather latency / issue (int8 probes, map L2-resident); no closed-form peak",
+                     "achieved": B * rollouts * nsteps * probes_pose / (ms * 1e-3) / 1e9, "peak": None,
+                     "unit": "G cell probes/s (upper bound: early exits probe less)", "frac": None, "traffic": None,
+                     "probes_per_pose": probes_pose, "probes_per_pose_reference_unpruned": probes_ref},
+    }
+    if world == 1:
+        from oracle import pyoracle
+        from oracle.pyoracle import Oracle, RefLib
+
+        pyoracle.build()
+        lib = RefLib if RefLib.available() else Oracle
+        sample = 2048 if dwa_mode else 200000
+        sub = slice(0, sample)
+        t0 = time.perf_counter()
+        if dwa_mode:
+            lib.dwa_control(data, res, -100.0, -100.0, colp, dwa_cfg, (3, 8, 5), x0[sub], u[sub], vref=np.zeros((sample, 3)))
+        else:
+            lib.validate_control(data, res, -100.0, -100.0, colp, x0[sub], u[sub], 0.1, 0.5)
+        dt_cpu = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sample / dt_cpu, "unit": unit, "cores": 1,
+                                "kind": "reference" if lib is RefLib else "port",
+                                "sample": f"{sample} robots of the same workload, the reference's own "
+                                          f"{'DynamicWindow::control' if dwa_mode else 'validate_control'} on one core "
+                                          "(includes one GridMap construction)"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "collide", "dwa"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "c3":
         return run_phik(args, rank, world, local_rank)
+    if args.workload in ("collide", "dwa"):
+        return run_avoid(args, rank, world, local_rank)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl, rank, world)

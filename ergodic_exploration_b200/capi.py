@@ -53,6 +53,15 @@ class EbCollision(C.Structure):
                 ("obstacle_threshold", C.c_double), ("occupied_threshold", C.c_double)]
 
 
+class EbDwa(C.Structure):
+    """struct eb_dwa (include/ergodic_b200.h)"""
+
+    _fields_ = [(n, C.c_double) for n in ("dt", "horizon", "acc_dt", "acc_lim_x", "acc_lim_y", "acc_lim_th",
+                                          "max_vel_x", "min_vel_x", "max_vel_y", "min_vel_y", "max_rot_vel",
+                                          "min_rot_vel")] + [(n, C.c_uint) for n in ("vx_samples", "vy_samples",
+                                                                                     "vth_samples")]
+
+
 class ErgodicB200Error(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"[eb_status {status}] {message}")
@@ -117,6 +126,12 @@ SIGNATURES = {
     "eb_basis_spatial_coeff_host": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, _vp, _vp, C.c_longlong, _vp]),
     "eb_target_fill_host": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_longlong, _vp]),
     "eb_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
+    "eb_dwa_control_twist_host": (C.c_int, [_vp, C.POINTER(EbCollision), C.POINTER(EbDwa), _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "eb_dwa_control_twist_dev": (C.c_int, [_vp, C.POINTER(EbCollision), C.POINTER(EbDwa), _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "eb_dwa_control_traj_host": (C.c_int, [_vp, C.POINTER(EbCollision), C.POINTER(EbDwa), _vp, _vp, _vp, C.c_int, C.c_int,
+                                           C.c_double, C.c_int, _vp, _vp, _vp]),
+    "eb_dwa_control_traj_dev": (C.c_int, [_vp, C.POINTER(EbCollision), C.POINTER(EbDwa), _vp, _vp, _vp, C.c_int, C.c_int,
+                                          C.c_double, C.c_int, _vp, _vp, _vp]),
     "eb_peer_blob_bytes": (C.c_int, []),
     "eb_peer_group_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_longlong, C.POINTER(_vp)]),
     "eb_peer_group_export": (C.c_int, [_vp, _vp]),

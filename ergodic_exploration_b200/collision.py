@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's occupancy-grid collision API over the C ABI.
 
 ``Collision`` (collision.hpp:85-165), ``GridMap`` (grid.hpp:80-260, the parts the
-checks read) and ``validate_control`` (numerics.hpp:312-330) keep the
+checks read), ``validate_control`` (numerics.hpp:312-330) and ``DynamicWindow``
+(dynamic_window.hpp:60-172) keep the
 reference's names and argument meaning for a BATCH of poses / candidate twists
 sharing one map.  numpy arrays go through the ``_host`` entry points, torch
 CUDA tensors through the ``_dev`` ones.  Everything is computed by
@@ -14,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import EbCollision, check
+from .capi import EbCollision, EbDwa, check
 
 try:
     import torch
@@ -135,3 +136,73 @@ def validate_control(collision: Collision, grid: GridMap, x0, u, dt: float, hori
     """numerics.hpp:312-330 for a batch: (B, 3) start poses and twists -> int32 (B,),
     1 = the twist held for |horizon / dt| steps stays collision free"""
     return grid._validate(collision, x0, u, dt, horizon)
+
+
+class DynamicWindow:
+    """Dynamic window approach for a batch of robots sharing one map (dynamic_window.hpp:60-65;
+    same constructor argument order).  ``control`` mirrors both reference overloads
+    (dynamic_window.cpp:93-139 with a reference twist, :141-187 with a reference trajectory)
+    and returns (found (B,), u_opt (B, 3)) -- numpy in, numpy out; torch CUDA in, torch out."""
+
+    def __init__(self, collision: Collision, dt: float, horizon: float, acc_dt: float, acc_lim_x: float,
+                 acc_lim_y: float, acc_lim_th: float, max_vel_x: float, min_vel_x: float, max_vel_y: float,
+                 min_vel_y: float, max_rot_vel: float, min_rot_vel: float, vx_samples: int, vy_samples: int,
+                 vth_samples: int):
+        self._lib = capi.load()
+        self.collision = collision
+        self.cfg = EbDwa(float(dt), float(horizon), float(acc_dt), float(acc_lim_x), float(acc_lim_y),
+                         float(acc_lim_th), float(max_vel_x), float(min_vel_x), float(max_vel_y), float(min_vel_y),
+                         float(max_rot_vel), float(min_rot_vel), int(vx_samples), int(vy_samples), int(vth_samples))
+
+    def timeStep(self) -> float:
+        return self.cfg.dt
+
+    def horizon(self) -> float:
+        return self.cfg.horizon
+
+    def steps(self) -> int:
+        return int(abs(self.cfg.horizon / self.cfg.dt))
+
+    def control(self, grid: GridMap, x0, vb, vref=None, xt_ref=None, dt_ref: float = 0.0, min_cost=None):
+        """vref: (B, 3) reference twists, or xt_ref: a reference trajectory (ncols, 3) shared by the batch
+        or (B, ncols, 3) per instance (e.g. ErgodicControl.optTraj()) with its time step dt_ref"""
+        if (vref is None) == (xt_ref is None):
+            raise ValueError("give either vref or xt_ref")
+        grid._stream()
+        col, cfg = C.byref(self.collision.cfg), C.byref(self.cfg)
+        if _is_cuda(x0):
+            n = x0.numel() // 3
+            found = torch.empty(n, dtype=torch.int32, device=x0.device)
+            u = torch.empty((n, 3), dtype=torch.float64, device=x0.device)
+            ref = vref if vref is not None else xt_ref
+            for t in (x0, vb, ref):
+                assert _is_cuda(t) and t.dtype == torch.float64 and t.is_contiguous()
+            mc = C.c_void_p(min_cost.data_ptr()) if min_cost is not None else None
+            P = lambda t: C.c_void_p(t.data_ptr())
+            if vref is not None:
+                check(self._lib.eb_dwa_control_twist_dev(grid._h, col, cfg, P(x0), P(vb), P(vref), n, P(found), P(u), mc))
+            else:
+                per = 1 if xt_ref.dim() == 3 else 0
+                ncols = xt_ref.shape[-2]
+                check(self._lib.eb_dwa_control_traj_dev(grid._h, col, cfg, P(x0), P(vb), P(xt_ref), ncols, per,
+                                                        float(dt_ref), n, P(found), P(u), mc))
+            return found, u
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, 3)
+        vb = np.ascontiguousarray(vb, dtype=np.float64).reshape(-1, 3)
+        n = len(x0)
+        found, u = np.empty(n, dtype=np.int32), np.empty((n, 3))
+        mc = min_cost.ctypes.data if min_cost is not None else None
+        if vref is not None:
+            vref = np.ascontiguousarray(vref, dtype=np.float64).reshape(-1, 3)
+            st = self._lib.eb_dwa_control_twist_host(grid._h, col, cfg, x0.ctypes.data, vb.ctypes.data, vref.ctypes.data,
+                                                     n, found.ctypes.data, u.ctypes.data, mc)
+        else:
+            xt = np.ascontiguousarray(xt_ref, dtype=np.float64)
+            per = 1 if xt.ndim == 3 else 0
+            st = self._lib.eb_dwa_control_traj_host(grid._h, col, cfg, x0.ctypes.data, vb.ctypes.data, xt.ctypes.data,
+                                                    xt.shape[-2], per, float(dt_ref), n, found.ctypes.data,
+                                                    u.ctypes.data, mc)
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(self._lib.eb_last_error().decode())
+        check(st)
+        return found, u

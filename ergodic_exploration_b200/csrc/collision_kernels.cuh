@@ -21,7 +21,8 @@
 //  * world2Grid casts floor() to unsigned (undefined for poses left of / below
 //    the map); the x86-64 behaviour -- wrap-around, i.e. the signed floor -- is
 //    what the CPU checker under tests restates and what is implemented here.
-// The pose chain of validate_control uses explicitly rounded multiplies / adds in
+// DynamicWindow::control (dynamic_window.cpp:93-287) runs on the same pieces (dwa_control_kernel).
+// The pose chain of validate_control / the window rollouts uses explicitly rounded multiplies / adds in
 // the reference's association order; sin / cos come from the CUDA library, so a
 // pose can differ from glibc's by an ulp or two (a cell index could differ only
 // for a pose within ~1e-15 of a cell edge).
@@ -122,6 +123,40 @@ __global__ void __launch_bounds__(128) collision_check_kernel(const CollisionPar
   p.out[i] = collision_check_pose(p, p.x0[(size_t)i * 3 + 0], p.x0[(size_t)i * 3 + 1]) ? 1 : 0;
 }
 
+// integrate_twist (numerics.hpp:273-298): body-frame displacement of one step of a constant
+// twist -- the same for every step -- with every operation explicitly rounded
+struct TwistStep
+{
+  double d0, d1, d2;
+  __device__ __forceinline__ TwistStep(double u0, double u1, double u2, double dt)
+  {
+    if (fabs(u2 - 0.0) < 1.0e-12)
+    {
+      d0 = __dmul_rn(u0, dt);
+      d1 = __dmul_rn(u1, dt);
+      d2 = 0.0;
+    }
+    else
+    {
+      const double vb0 = __dmul_rn(u0, dt), vb1 = __dmul_rn(u1, dt), vb2 = __dmul_rn(u2, dt);
+      double s, c;
+      sincos(vb2, &s, &c);
+      d0 = __ddiv_rn(__dadd_rn(__dmul_rn(vb0, s), __dmul_rn(vb1, __dsub_rn(c, 1.0))), vb2);
+      d1 = __ddiv_rn(__dadd_rn(__dmul_rn(vb1, s), __dmul_rn(vb0, __dsub_rn(1.0, c))), vb2);
+      d2 = vb2;
+    }
+  }
+  // x + transform2d(theta) * dqb, rows summed in column order (the third column is zero), then the wrap
+  __device__ __forceinline__ void advance(double& x, double& y, double& th) const
+  {
+    double s, c;
+    sincos(th, &s, &c);
+    x = __dadd_rn(x, __dadd_rn(__dmul_rn(c, d0), __dmul_rn(-s, d1)));
+    y = __dadd_rn(y, __dadd_rn(__dmul_rn(s, d0), __dmul_rn(c, d1)));
+    th = normalize_angle_pi_rn(__dadd_rn(th, d2));
+  }
+};
+
 // validate_control (numerics.hpp:312-330): constant twist integrated for `steps` steps,
 // the pose checked after every step; 1 = collision free
 __global__ void __launch_bounds__(128) validate_control_kernel(const CollisionParams p)
@@ -129,33 +164,11 @@ __global__ void __launch_bounds__(128) validate_control_kernel(const CollisionPa
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.B) return;
   double x = p.x0[(size_t)i * 3 + 0], y = p.x0[(size_t)i * 3 + 1], th = p.x0[(size_t)i * 3 + 2];
-  const double u0 = p.u[(size_t)i * 3 + 0], u1 = p.u[(size_t)i * 3 + 1], u2 = p.u[(size_t)i * 3 + 2];
-  // integrate_twist (:273-298): the body-frame displacement of one step is the same every step
-  double d0, d1, d2;
-  if (fabs(u2 - 0.0) < 1.0e-12)
-  {
-    d0 = __dmul_rn(u0, p.dt);
-    d1 = __dmul_rn(u1, p.dt);
-    d2 = 0.0;
-  }
-  else
-  {
-    const double vb0 = __dmul_rn(u0, p.dt), vb1 = __dmul_rn(u1, p.dt), vb2 = __dmul_rn(u2, p.dt);
-    double s, c;
-    sincos(vb2, &s, &c);
-    d0 = __ddiv_rn(__dadd_rn(__dmul_rn(vb0, s), __dmul_rn(vb1, __dsub_rn(c, 1.0))), vb2);
-    d1 = __ddiv_rn(__dadd_rn(__dmul_rn(vb1, s), __dmul_rn(vb0, __dsub_rn(1.0, c))), vb2);
-    d2 = vb2;
-  }
+  const TwistStep step(p.u[(size_t)i * 3 + 0], p.u[(size_t)i * 3 + 1], p.u[(size_t)i * 3 + 2], p.dt);
   int ok = 1;
   for (int k = 0; k < p.steps; k++)
   {
-    double s, c;
-    sincos(th, &s, &c);
-    // x + transform2d(theta) * dqb, rows summed in column order (the third column is zero)
-    x = __dadd_rn(x, __dadd_rn(__dmul_rn(c, d0), __dmul_rn(-s, d1)));
-    y = __dadd_rn(y, __dadd_rn(__dmul_rn(s, d0), __dmul_rn(c, d1)));
-    th = normalize_angle_pi_rn(__dadd_rn(th, d2));
+    step.advance(x, y, th);
     if (collision_check_pose(p, x, y))
     {
       ok = 0;
@@ -163,5 +176,119 @@ __global__ void __launch_bounds__(128) validate_control_kernel(const CollisionPa
     }
   }
   p.out[i] = ok;
+}
+
+// ---- DynamicWindow::control (dynamic_window.cpp:93-187) ---------------------------------
+// One warp per instance; the lanes stride over the vx * vy * vth candidate twists of the
+// window (:189-235), each lane rolls its candidates out (objective :237-286: constant twist,
+// collision check per step, tracking cost) and keeps its first strict minimum; a warp arg-min
+// with ties to the lower candidate index reproduces the reference's loop order exactly.
+// The candidate twists are the reference's accumulated sums (vx += dvx, ...).
+struct DwaParams
+{
+  CollisionParams col;  // grid, radii, threshold, steps, dt (B, x0, u, out unused)
+  int B;
+  double acc_dt, acc_lim[3], vmin[3], vmax[3];
+  unsigned int n[3];    // vx, vy, vth samples (>= 1)
+  const double* x0;     // [B][3]
+  const double* vb;     // [B][3] current body twist
+  const double* vref;   // [B][3] reference twist, or null
+  const double* xt_ref; // reference trajectory [ncols][3] (xt_stride = 0: shared) or [B][ncols][3]
+  int ncols;
+  long long xt_stride;
+  double tf;            // ncols * dt_ref (:148)
+  int* found;           // [B]
+  double* u_opt;        // [B][3]
+  double* min_cost;     // [B] or null
+};
+
+constexpr double kDblMax = 1.7976931348623157e308;
+
+__device__ __forceinline__ double dwa_objective(const DwaParams& p, const double* xt, double x, double y, double th,
+                                                double u0, double u1, double u2, const double* vref)
+{
+  const TwistStep step(u0, u1, u2, p.col.dt);
+  double t = 0.0, cost = 0.0;
+  for (int k = 0; k < p.col.steps; k++)
+  {
+    step.advance(x, y, th);
+    if (collision_check_pose(p.col, x, y)) return kDblMax;
+    if (xt)
+    {
+      // index into the reference trajectory (:276)
+      const unsigned int j = (unsigned int)round(__ddiv_rn(__dmul_rn((double)(p.ncols - 1), t), p.tf));
+      const double dx = __dsub_rn(xt[3 * (size_t)j + 0], x), dy = __dsub_rn(xt[3 * (size_t)j + 1], y);
+      cost = __dadd_rn(cost, __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+      cost = __dadd_rn(cost, fabs(normalize_angle_pi_rn(__dsub_rn(normalize_angle_pi_rn(xt[3 * (size_t)j + 2]), th))));
+      t = __dadd_rn(t, p.col.dt);
+    }
+  }
+  if (xt) return cost;
+  const double e0 = __dsub_rn(vref[0], u0), e1 = __dsub_rn(vref[1], u1), e2 = __dsub_rn(vref[2], u2);
+  return __dadd_rn(__dadd_rn(__dmul_rn(e0, e0), __dmul_rn(e1, e1)), __dmul_rn(e2, e2));
+}
+
+__global__ void __launch_bounds__(128) dwa_control_kernel(const DwaParams p)
+{
+  const int lane = threadIdx.x & 31;
+  const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (inst >= p.B) return;
+  const double x = p.x0[(size_t)inst * 3 + 0], y = p.x0[(size_t)inst * 3 + 1], th = p.x0[(size_t)inst * 3 + 2];
+  // DynamicWindow::window (:189-235)
+  double lower[3], delta[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+  {
+    const double v = p.vb[(size_t)inst * 3 + a], reach = __dmul_rn(p.acc_lim[a], p.acc_dt);
+    lower[a] = fmax(__dsub_rn(v, reach), p.vmin[a]);
+    const double upper = fmin(__dadd_rn(v, reach), p.vmax[a]);
+    delta[a] = p.n[a] > 1 ? __ddiv_rn(__dsub_rn(upper, lower[a]), (double)(p.n[a] - 1)) : 0.0;
+  }
+  const double* xt = p.xt_ref ? p.xt_ref + (size_t)inst * (size_t)p.xt_stride : nullptr;
+  const double* vref = p.vref ? p.vref + (size_t)inst * 3 : nullptr;
+  const unsigned int total = p.n[0] * p.n[1] * p.n[2];
+  auto twist = [&](unsigned int c, double& u0, double& u1, double& u2) {
+    const unsigned int k = c % p.n[2], j = (c / p.n[2]) % p.n[1], i = c / (p.n[2] * p.n[1]);
+    u0 = lower[0];
+    for (unsigned int s = 0; s < i; s++) u0 = __dadd_rn(u0, delta[0]);  // vx += dvx, i times
+    u1 = lower[1];
+    for (unsigned int s = 0; s < j; s++) u1 = __dadd_rn(u1, delta[1]);
+    u2 = lower[2];
+    for (unsigned int s = 0; s < k; s++) u2 = __dadd_rn(u2, delta[2]);
+  };
+  double best = kDblMax;
+  unsigned int best_c = 0xffffffffu;
+  for (unsigned int c = lane; c < total; c += 32)
+  {
+    double u0, u1, u2;
+    twist(c, u0, u1, u2);
+    const double cost = dwa_objective(p, xt, x, y, th, u0, u1, u2, vref);
+    if (cost < best)
+    {
+      best = cost;
+      best_c = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    const double oc = __shfl_xor_sync(kFull, best, o);
+    const unsigned int oi = __shfl_xor_sync(kFull, best_c, o);
+    if (oc < best || (oc == best && oi < best_c))
+    {
+      best = oc;
+      best_c = oi;
+    }
+  }
+  if (lane == 0)
+  {
+    double u0 = 0.0, u1 = 0.0, u2 = 0.0;  // u_opt stays zero when nothing beats the initial min_cost (:99)
+    if (best_c != 0xffffffffu) twist(best_c, u0, u1, u2);
+    p.u_opt[(size_t)inst * 3 + 0] = u0;
+    p.u_opt[(size_t)inst * 3 + 1] = u1;
+    p.u_opt[(size_t)inst * 3 + 2] = u2;
+    p.found[inst] = (fabs(best - kDblMax) < 1.0e-12) ? 0 : 1;  // almost_equal(min_cost, max) (:132)
+    if (p.min_cost) p.min_cost[inst] = best;
+  }
 }
 }  // namespace eb

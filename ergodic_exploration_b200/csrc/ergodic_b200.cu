@@ -1449,6 +1449,143 @@ eb_status eb_validate_control_host(eb_grid* g, const eb_collision* c, const doub
   return EB_OK;
 }
 
+// ---- DynamicWindow::control (dynamic_window.cpp:93-187) -----------------------------
+}  // extern "C"
+
+namespace
+{
+eb_status dwa_params(const eb_grid* g, const eb_collision* c, const eb_dwa* d, int count, eb::DwaParams* p)
+{
+  if (!d) return fail(EB_ERR_INVALID_ARGUMENT, "dwa is NULL");
+  eb_status st = collision_params(g, c, &p->col);
+  if (st != EB_OK) return st;
+  if (count < 0 || d->dt == 0.0) return fail(EB_ERR_INVALID_ARGUMENT, "eb_dwa_control: bad arguments");
+  p->col.dt = d->dt;
+  p->col.steps = (int)static_cast<unsigned int>(std::abs(d->horizon / d->dt));  // dynamic_window.cpp:69
+  p->B = count;
+  p->acc_dt = d->acc_dt;
+  const double acc[3] = { d->acc_lim_x, d->acc_lim_y, d->acc_lim_th };
+  const double vmin[3] = { d->min_vel_x, d->min_vel_y, d->min_rot_vel };
+  const double vmax[3] = { d->max_vel_x, d->max_vel_y, d->max_rot_vel };
+  const unsigned int n[3] = { d->vx_samples, d->vy_samples, d->vth_samples };
+  for (int a = 0; a < 3; a++)
+  {
+    p->acc_lim[a] = acc[a];
+    p->vmin[a] = vmin[a];
+    p->vmax[a] = vmax[a];
+    p->n[a] = n[a] ? n[a] : 1u;  // dynamic_window.cpp:71-91: 0 samples -> 1
+  }
+  return EB_OK;
+}
+
+eb_status dwa_launch(eb_grid* g, eb::DwaParams& p)
+{
+  if (p.B == 0) return EB_OK;
+  EB_CUDA(cudaSetDevice(g->device));
+  const int threads = 128, warps_per_block = threads / 32;
+  eb::dwa_control_kernel<<<(p.B + warps_per_block - 1) / warps_per_block, threads, 0, g->stream>>>(p);
+  EB_CUDA(cudaGetLastError());
+  g->launches += 1;
+  return EB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+eb_status eb_dwa_control_twist_dev(eb_grid* g, const eb_collision* c, const eb_dwa* d, const double* x0_dev,
+                                   const double* vb_dev, const double* vref_dev, int count, int* found_dev,
+                                   double* u_opt_dev, double* min_cost_dev)
+{
+  eb::DwaParams p{};
+  eb_status st = dwa_params(g, c, d, count, &p);
+  if (st != EB_OK) return st;
+  if (count > 0 && (!x0_dev || !vb_dev || !vref_dev || !found_dev || !u_opt_dev))
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_dwa_control_twist: NULL argument");
+  p.x0 = x0_dev;
+  p.vb = vb_dev;
+  p.vref = vref_dev;
+  p.found = found_dev;
+  p.u_opt = u_opt_dev;
+  p.min_cost = min_cost_dev;
+  return dwa_launch(g, p);
+}
+
+eb_status eb_dwa_control_traj_dev(eb_grid* g, const eb_collision* c, const eb_dwa* d, const double* x0_dev,
+                                  const double* vb_dev, const double* xt_ref_dev, int ncols, int per_instance,
+                                  double dt_ref, int count, int* found_dev, double* u_opt_dev, double* min_cost_dev)
+{
+  eb::DwaParams p{};
+  eb_status st = dwa_params(g, c, d, count, &p);
+  if (st != EB_OK) return st;
+  if (ncols < 1 || (count > 0 && (!x0_dev || !vb_dev || !xt_ref_dev || !found_dev || !u_opt_dev)))
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_dwa_control_traj: bad arguments");
+  p.x0 = x0_dev;
+  p.vb = vb_dev;
+  p.xt_ref = xt_ref_dev;
+  p.ncols = ncols;
+  p.xt_stride = per_instance ? 3LL * ncols : 0LL;
+  p.tf = static_cast<double>(ncols) * dt_ref;  // dynamic_window.cpp:148
+  p.found = found_dev;
+  p.u_opt = u_opt_dev;
+  p.min_cost = min_cost_dev;
+  return dwa_launch(g, p);
+}
+
+static eb_status dwa_host(eb_grid* g, const eb_collision* c, const eb_dwa* d, const double* x0, const double* vb,
+                          const double* ref, size_t ref_doubles, bool traj, int ncols, int per_instance, double dt_ref,
+                          int count, int* found, double* u_opt, double* min_cost)
+{
+  if (!g) return fail(EB_ERR_INVALID_ARGUMENT, "grid is NULL");
+  if (count < 0 || (count > 0 && (!x0 || !vb || !ref || !found || !u_opt)))
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_dwa_control_host: bad arguments");
+  if (count == 0) return EB_OK;
+  EB_CUDA(cudaSetDevice(g->device));
+  DevBuf dx, dv, dr, du, dc;
+  int* dfound = nullptr;
+  EB_CUDA(dx.alloc(3 * (size_t)count));
+  EB_CUDA(dv.alloc(3 * (size_t)count));
+  EB_CUDA(dr.alloc(ref_doubles));
+  EB_CUDA(du.alloc(3 * (size_t)count));
+  EB_CUDA(dc.alloc((size_t)count));
+  EB_CUDA(cudaMalloc(&dfound, sizeof(int) * (size_t)count));
+  auto done = [&](eb_status st) {
+    cudaFree(dfound);
+    return st;
+  };
+  cudaError_t e = cudaMemcpyAsync(dx.p, x0, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dv.p, vb, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dr.p, ref, sizeof(double) * ref_doubles, cudaMemcpyHostToDevice, g->stream);
+  if (e != cudaSuccess) return done(fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e)));
+  eb_status st = traj ? eb_dwa_control_traj_dev(g, c, d, dx.p, dv.p, dr.p, ncols, per_instance, dt_ref, count, dfound,
+                                                du.p, dc.p) :
+                        eb_dwa_control_twist_dev(g, c, d, dx.p, dv.p, dr.p, count, dfound, du.p, dc.p);
+  if (st != EB_OK) return done(st);
+  e = cudaMemcpyAsync(found, dfound, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(u_opt, du.p, sizeof(double) * 3 * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
+  if (e == cudaSuccess && min_cost)
+    e = cudaMemcpyAsync(min_cost, dc.p, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+  if (e != cudaSuccess) return done(fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e)));
+  return done(EB_OK);
+}
+
+eb_status eb_dwa_control_twist_host(eb_grid* g, const eb_collision* c, const eb_dwa* d, const double* x0,
+                                    const double* vb, const double* vref, int count, int* found, double* u_opt,
+                                    double* min_cost)
+{
+  return dwa_host(g, c, d, x0, vb, vref, 3 * (size_t)std::max(count, 0), false, 0, 0, 0.0, count, found, u_opt, min_cost);
+}
+
+eb_status eb_dwa_control_traj_host(eb_grid* g, const eb_collision* c, const eb_dwa* d, const double* x0,
+                                   const double* vb, const double* xt_ref, int ncols, int per_instance, double dt_ref,
+                                   int count, int* found, double* u_opt, double* min_cost)
+{
+  if (ncols < 1) return fail(EB_ERR_INVALID_ARGUMENT, "eb_dwa_control_traj_host: ncols < 1");
+  const size_t ref_doubles = 3 * (size_t)ncols * (per_instance ? (size_t)std::max(count, 0) : 1);
+  return dwa_host(g, c, d, x0, vb, xt_ref, ref_doubles, true, ncols, per_instance, dt_ref, count, found, u_opt,
+                  min_cost);
+}
+
 eb_status eb_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops)
 {
   EB_CUDA(cudaSetDevice(device));

@@ -269,6 +269,34 @@ eb_status eb_validate_control_dev(eb_grid *g, const eb_collision *c, const doubl
                                   int count, double dt, double horizon, int *valid_dev);
 long long eb_grid_launch_count(const eb_grid *g);
 
+/* ---- DynamicWindow -----------------------------------
+ * Batched DynamicWindow::control (dynamic_window.cpp:93-187): for every instance the
+ * vx x vy x vth candidate twists of its dynamic window (:189-235) are rolled out as
+ * constant twists with a collision check per step (objective :237-286) and the first
+ * minimum-cost collision-free twist in the reference's loop order is returned.
+ * eb_dwa = the constructor arguments after `collision` (dynamic_window.hpp:60-65). */
+typedef struct eb_dwa {
+  double dt, horizon, acc_dt, acc_lim_x, acc_lim_y, acc_lim_th;
+  double max_vel_x, min_vel_x, max_vel_y, min_vel_y, max_rot_vel, min_rot_vel;
+  unsigned int vx_samples, vy_samples, vth_samples; /* 0 is promoted to 1 (:71-91) */
+} eb_dwa;
+/* control(grid, x0, vb, vref) :93-139 -- x0, vb, vref, u_opt: 3 x count; found[i] = 0 when no twist is
+ * collision free (u_opt = 0); min_cost may be NULL */
+eb_status eb_dwa_control_twist_host(eb_grid *g, const eb_collision *c, const eb_dwa *d, const double *x0,
+                                    const double *vb, const double *vref, int count, int *found, double *u_opt,
+                                    double *min_cost);
+eb_status eb_dwa_control_twist_dev(eb_grid *g, const eb_collision *c, const eb_dwa *d, const double *x0_dev,
+                                   const double *vb_dev, const double *vref_dev, int count, int *found_dev,
+                                   double *u_opt_dev, double *min_cost_dev);
+/* control(grid, x0, vb, xt_ref, dt_ref) :141-187 -- xt_ref is 3 x ncols, one trajectory for the whole batch
+ * (per_instance = 0) or 3 x ncols x count, e.g. the output of eb_opt_traj_dev (per_instance = 1) */
+eb_status eb_dwa_control_traj_host(eb_grid *g, const eb_collision *c, const eb_dwa *d, const double *x0,
+                                   const double *vb, const double *xt_ref, int ncols, int per_instance,
+                                   double dt_ref, int count, int *found, double *u_opt, double *min_cost);
+eb_status eb_dwa_control_traj_dev(eb_grid *g, const eb_collision *c, const eb_dwa *d, const double *x0_dev,
+                                  const double *vb_dev, const double *xt_ref_dev, int ncols, int per_instance,
+                                  double dt_ref, int count, int *found_dev, double *u_opt_dev, double *min_cost_dev);
+
 /* ---- measurement helper --------------------------------------------------
  * Measured FP64 throughput of the device (TFLOP/s, 2 flop per FMA): a
  * register-resident DFMA loop and an mma.sync m8n8k4 f64 (DMMA) loop.  Used

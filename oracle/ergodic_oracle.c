@@ -12,6 +12,7 @@
  */
 #include "ergodic_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -128,6 +129,97 @@ int eo_validate_control(const eo_grid *g, const eo_collision *c, const double x0
     if (eo_collision_check(g, c, x)) return 0;
   }
   return 1;
+}
+
+/* ------------------------------------------------------------------------ */
+/* DynamicWindow                                                            */
+/* ------------------------------------------------------------------------ */
+
+/* DynamicWindow::window dynamic_window.cpp:189-235 */
+static void dwa_window(const eo_dwa *d, const double vb[3], unsigned int n[3], double lower[3], double delta[3])
+{
+  n[0] = d->vx_samples ? d->vx_samples : 1u;
+  n[1] = d->vy_samples ? d->vy_samples : 1u;
+  n[2] = d->vth_samples ? d->vth_samples : 1u;
+  const double acc[3] = { d->acc_lim_x, d->acc_lim_y, d->acc_lim_th };
+  const double vmin[3] = { d->min_vel_x, d->min_vel_y, d->min_rot_vel };
+  const double vmax[3] = { d->max_vel_x, d->max_vel_y, d->max_rot_vel };
+  for (int a = 0; a < 3; a++) {
+    lower[a] = fmax(vb[a] - acc[a] * d->acc_dt, vmin[a]);
+    const double upper = fmin(vb[a] + acc[a] * d->acc_dt, vmax[a]);
+    delta[a] = n[a] > 1 ? (upper - lower[a]) / (double)(n[a] - 1) : 0.0;
+  }
+}
+
+/* the two objectives (:237-257, :259-286); DBL_MAX on collision */
+static double dwa_objective(const eo_grid *g, const eo_collision *c, const eo_dwa *d, const double x0[3],
+                            const double u[3], const double *vref, const double *xt_ref, int ncols, double tf)
+{
+  double pose[3] = { x0[0], x0[1], x0[2] };
+  const unsigned int steps = (unsigned int)fabs(d->horizon / d->dt);
+  double t = 0.0, cost = 0.0;
+  for (unsigned int i = 0; i < steps; i++) {
+    double pn[3];
+    eo_integrate_twist(pose, u, d->dt, pn);
+    pn[2] = eo_normalize_angle_pi(pn[2]);
+    memcpy(pose, pn, sizeof(pose));
+    if (eo_collision_check(g, c, pose)) return DBL_MAX;
+    if (xt_ref) {
+      const unsigned int j = (unsigned int)round((double)(ncols - 1) * t / tf);
+      const double dx = xt_ref[3 * j + 0] - pose[0], dy = xt_ref[3 * j + 1] - pose[1];
+      cost += sqrt(dx * dx + dy * dy);
+      cost += fabs(eo_normalize_angle_pi(eo_normalize_angle_pi(xt_ref[3 * j + 2]) - pose[2]));
+      t += d->dt;
+    }
+  }
+  if (xt_ref) return cost;
+  const double e0 = vref[0] - u[0], e1 = vref[1] - u[1], e2 = vref[2] - u[2];
+  return (e0 * e0 + e1 * e1) + e2 * e2;
+}
+
+static int dwa_search(const eo_grid *g, const eo_collision *c, const eo_dwa *d, const double x0[3],
+                      const double vb[3], const double *vref, const double *xt_ref, int ncols, double tf,
+                      double u_opt[3], double *min_cost_out)
+{
+  unsigned int n[3];
+  double lower[3], delta[3];
+  dwa_window(d, vb, n, lower, delta);
+  double min_cost = DBL_MAX;
+  u_opt[0] = u_opt[1] = u_opt[2] = 0.0;
+  double vx = lower[0];
+  for (unsigned int i = 0; i < n[0]; i++) {
+    double vy = lower[1];
+    for (unsigned int j = 0; j < n[1]; j++) {
+      double w = lower[2];
+      for (unsigned int k = 0; k < n[2]; k++) {
+        const double u[3] = { vx, vy, w };
+        const double cost = dwa_objective(g, c, d, x0, u, vref, xt_ref, ncols, tf);
+        if (cost < min_cost) {
+          min_cost = cost;
+          memcpy(u_opt, u, sizeof(u));
+        }
+        w += delta[2];
+      }
+      vy += delta[1];
+    }
+    vx += delta[0];
+  }
+  if (min_cost_out) *min_cost_out = min_cost;
+  return eo_almost_equal(min_cost, DBL_MAX, 1.0e-12) ? 0 : 1;
+}
+
+int eo_dwa_control_twist(const eo_grid *g, const eo_collision *c, const eo_dwa *d, const double x0[3],
+                         const double vb[3], const double vref[3], double u_opt[3], double *min_cost)
+{
+  return dwa_search(g, c, d, x0, vb, vref, NULL, 0, 0.0, u_opt, min_cost);
+}
+
+int eo_dwa_control_traj(const eo_grid *g, const eo_collision *c, const eo_dwa *d, const double x0[3],
+                        const double vb[3], const double *xt_ref, int ncols, double dt_ref,
+                        double u_opt[3], double *min_cost)
+{
+  const double tf = (double)ncols * dt_ref; /* :148 */
+  return dwa_search(g, c, d, x0, vb, NULL, xt_ref, ncols, tf, u_opt, min_cost);
 }
 
 /* ------------------------------------------------------------------------ */

@@ -126,6 +126,22 @@ int eo_collision_check(const eo_grid *g, const eo_collision *c, const double pos
 int eo_validate_control(const eo_grid *g, const eo_collision *c, const double x0[3],
                         const double u[3], double dt, double horizon);
 
+/* ---- DynamicWindow (dynamic_window.hpp:60-172) ----- */
+typedef struct eo_dwa {
+  double dt, horizon, acc_dt, acc_lim_x, acc_lim_y, acc_lim_th;
+  double max_vel_x, min_vel_x, max_vel_y, min_vel_y, max_rot_vel, min_rot_vel;
+  unsigned int vx_samples, vy_samples, vth_samples; /* 0 is promoted to 1 (dynamic_window.cpp:71-91) */
+} eo_dwa;
+/* DynamicWindow::control(grid, x0, vb, vref) dynamic_window.cpp:93-139 (window :189-235,
+ * objective :237-257); returns 1 if a collision-free twist exists; u_opt, min_cost out */
+int eo_dwa_control_twist(const eo_grid *g, const eo_collision *c, const eo_dwa *d, const double x0[3],
+                         const double vb[3], const double vref[3], double u_opt[3], double *min_cost);
+/* DynamicWindow::control(grid, x0, vb, xt_ref, dt_ref) :141-187 (objective :259-286);
+ * xt_ref is 3 x ncols column-major */
+int eo_dwa_control_traj(const eo_grid *g, const eo_collision *c, const eo_dwa *d, const double x0[3],
+                        const double vb[3], const double *xt_ref, int ncols, double dt_ref,
+                        double u_opt[3], double *min_cost);
+
 typedef struct eo_controller eo_controller;
 
 /* ctor :188-222.  Rinv is 3x3 column-major.  Returns NULL when steps==1

@@ -359,6 +359,41 @@ class Oracle:
                          for i in range(len(x0))], dtype=np.int32)
 
 
+    # ---- DynamicWindow --------------------------------
+    class _Dwa(C.Structure):
+        _fields_ = [(n, C.c_double) for n in ("dt", "horizon", "acc_dt", "acc_lim_x", "acc_lim_y", "acc_lim_th",
+                                              "max_vel_x", "min_vel_x", "max_vel_y", "min_vel_y", "max_rot_vel",
+                                              "min_rot_vel")] + [(n, C.c_uint) for n in ("vx", "vy", "vth")]
+
+    @classmethod
+    def dwa_control(cls, data, res, xmin, ymin, col, dwa_cfg, samples, x0, vb, vref=None, xt_ref=None, dt_ref=0.1):
+        """dwa_cfg = the 12 doubles of the DynamicWindow constructor after `collision`
+        (dynamic_window.hpp:60-65), samples = (vx, vy, vth).  vref: (B, 3) reference twists, or
+        xt_ref: (ncols, 3) one reference trajectory.  -> found (B,), u_opt (B, 3), min_cost (B,)"""
+        data, g, c = cls._grid_args(data, res, xmin, ymin, col)
+        d = cls._Dwa(*[float(v) for v in dwa_cfg], *[int(v) for v in samples])
+        x0, _ = _d(x0); vb, _ = _d(vb)
+        x0, vb = x0.reshape(-1, 3), vb.reshape(-1, 3)
+        n = len(x0)
+        found, u, cost = np.zeros(n, dtype=np.int32), np.zeros((n, 3)), np.zeros(n)
+        lib = cls.lib()
+        if vref is not None:
+            vref, _ = _d(vref); vref = vref.reshape(-1, 3)
+            f = lib.eo_dwa_control_twist
+            f.argtypes = [C.c_void_p] * 3 + [_dp] * 5
+            for i in range(n):
+                found[i] = f(C.byref(g), C.byref(c), C.byref(d), x0[i].ctypes.data_as(_dp), vb[i].ctypes.data_as(_dp),
+                             vref[i].ctypes.data_as(_dp), u[i].ctypes.data_as(_dp), cost[i:].ctypes.data_as(_dp))
+        else:
+            xt, pxt = _d(xt_ref)
+            f = lib.eo_dwa_control_traj
+            f.argtypes = [C.c_void_p] * 3 + [_dp] * 3 + [C.c_int, C.c_double, _dp, _dp]
+            for i in range(n):
+                found[i] = f(C.byref(g), C.byref(c), C.byref(d), x0[i].ctypes.data_as(_dp), vb[i].ctypes.data_as(_dp),
+                             pxt, xt.shape[0], float(dt_ref), u[i].ctypes.data_as(_dp), cost[i:].ctypes.data_as(_dp))
+        return found, u, cost
+
+
 class RefLib:
     """The unmodified reference, compiled against the shim."""
 
@@ -541,3 +576,24 @@ class RefLib:
              dt, horizon, valid.ctypes.data_as(_ip)) != 0:
             raise ValueError(cls.lib().ref_last_error().decode())
         return valid
+
+    @classmethod
+    def dwa_control(cls, data, res, xmin, ymin, col, dwa_cfg, samples, x0, vb, vref=None, xt_ref=None, dt_ref=0.1):
+        """the reference's own DynamicWindow::control (both overloads); -> found (B,), u_opt (B, 3)"""
+        data = np.ascontiguousarray(data, dtype=np.int8)
+        x0, px = _d(x0); vb, pv = _d(vb)
+        n = x0.size // 3
+        colv, pc = _d(col); cfg, pcfg = _d(dwa_cfg)
+        smp = np.ascontiguousarray(samples, dtype=np.uint32)
+        found, u = np.zeros(n, dtype=np.int32), np.zeros((n, 3))
+        f = cls.lib().ref_dwa_control_many
+        f.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, _dp, _dp, C.c_void_p, _dp, _dp,
+                      C.c_int, C.c_int, _dp, C.c_int, C.c_double, _ip, _dp]
+        if vref is not None:
+            ref, pr = _d(vref); mode, ncols = 0, 0
+        else:
+            ref, pr = _d(xt_ref); mode, ncols = 1, ref.shape[0]
+        if f(data.ctypes.data, data.shape[1], data.shape[0], res, xmin, ymin, pc, pcfg, smp.ctypes.data, px, pv, n, mode,
+             pr, ncols, float(dt_ref), found.ctypes.data_as(_ip), u.ctypes.data_as(_dp)) != 0:
+            raise ValueError(cls.lib().ref_last_error().decode())
+        return found, u

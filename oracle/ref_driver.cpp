@@ -32,6 +32,7 @@
 #include <ergodic_exploration/ergodic_control.hpp>
 #include <ergodic_exploration/models/cart.hpp>
 #include <ergodic_exploration/models/omni.hpp>
+#include <ergodic_exploration/dynamic_window.hpp>
 #undef private
 
 using arma::mat;
@@ -450,6 +451,42 @@ int ref_validate_control_many(const signed char* data, unsigned xsize, unsigned 
     const ee::Collision col(boundary_radius, search_radius, obstacle_threshold, occupied_threshold);
     for (int i = 0; i < count; i++)
       valid[i] = ee::validate_control(col, grid, v3(x0 + 3 * i), v3(u + 3 * i), dt, horizon) ? 1 : 0;
+    return 0;
+  }
+  catch (const std::exception& e)
+  {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// ---- DynamicWindow (dynamic_window.cpp): cfg = {dt, horizon, acc_dt, acc_lim_x, acc_lim_y, acc_lim_th,
+//      max_vel_x, min_vel_x, max_vel_y, min_vel_y, max_rot_vel, min_rot_vel}, samples = {vx, vy, vth};
+//      mode 0: vref (3 x count twists), mode 1: one reference trajectory xt_ref (3 x ncols) for every instance
+int ref_dwa_control_many(const signed char* data, unsigned xsize, unsigned ysize, double res, double xmin, double ymin,
+                         const double* col, const double* cfg, const unsigned* samples, const double* x0,
+                         const double* vb, int count, int mode, const double* ref, int ncols, double dt_ref,
+                         int* found, double* u_opt)
+{
+  try
+  {
+    const ee::GridMap grid = occupancy_grid(data, xsize, ysize, res, xmin, ymin);
+    const ee::Collision collision(col[0], col[1], col[2], col[3]);
+    const ee::DynamicWindow dwa(collision, cfg[0], cfg[1], cfg[2], cfg[3], cfg[4], cfg[5], cfg[6], cfg[7], cfg[8],
+                                cfg[9], cfg[10], cfg[11], samples[0], samples[1], samples[2]);
+    mat xt_ref;
+    if (mode == 1)
+    {
+      xt_ref.set_size(3, ncols);
+      std::memcpy(xt_ref.memptr(), ref, sizeof(double) * 3 * ncols);
+    }
+    for (int i = 0; i < count; i++)
+    {
+      const auto r = mode == 0 ? dwa.control(grid, v3(x0 + 3 * i), v3(vb + 3 * i), v3(ref + 3 * i)) :
+                                 dwa.control(grid, v3(x0 + 3 * i), v3(vb + 3 * i), xt_ref, dt_ref);
+      found[i] = std::get<0>(r) ? 1 : 0;
+      out_mat(std::get<1>(r), u_opt + 3 * i);
+    }
     return 0;
   }
   catch (const std::exception& e)

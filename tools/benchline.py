@@ -8,4 +8,4 @@ r = d.get("roofline", {})
 e = d.get("e2e", {})
 print("%-42s value %.4g %s  ms/step %.4f  kernel_ms %.4f  frac %.3f  e2e %.4g" % (
     d["config"]["workload"][:42], d["value"], d["unit"], d["ms_per_step"], r.get("kernel_ms", float("nan")),
-    r.get("frac", float("nan")), e.get("value", float("nan"))))
+    r.get("frac") or float("nan"), e.get("value", float("nan"))))
