@@ -146,6 +146,7 @@ SIGNATURES = {
     "eb_grid_destroy": (None, [_vp]),
     "eb_grid_set_stream": (C.c_int, [_vp, _vp]),
     "eb_grid_launch_count": (C.c_longlong, [_vp]),
+    "eb_grid_set_dilation": (C.c_int, [_vp, C.c_int]),
     "eb_collision_check_host": (C.c_int, [_vp, C.POINTER(EbCollision), _vp, C.c_int, _vp]),
     "eb_collision_check_dev": (C.c_int, [_vp, C.POINTER(EbCollision), _vp, C.c_int, _vp]),
     "eb_validate_control_host": (C.c_int, [_vp, C.POINTER(EbCollision), _vp, _vp, C.c_int, C.c_double, C.c_double, _vp]),

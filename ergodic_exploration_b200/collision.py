@@ -91,6 +91,10 @@ class GridMap:
     def launch_count(self) -> int:
         return int(self._lib.eb_grid_launch_count(self._h))
 
+    def dilation(self, mode: int) -> None:
+        """0 = automatic, 1 = always walk the circles, 2 = always use the pre-dilated map"""
+        check(self._lib.eb_grid_set_dilation(self._h, int(mode)))
+
     def _stream(self):
         if torch is not None and torch.cuda.is_available():
             s = torch.cuda.current_stream(self.device).cuda_stream

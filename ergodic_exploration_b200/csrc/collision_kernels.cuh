@@ -53,6 +53,9 @@ struct CollisionParams
   const double* x0;  // [B][3] start poses (validate) or the poses themselves (check)
   const double* u;   // [B][3] twists (validate only)
   int* out;          // [B]: collision_check 1 = collision; validate_control 1 = collision free
+  // optional pre-dilated map (inflate_kernel): one lookup answers collisionCheck for a centre cell
+  const unsigned char* inflated;  // [ysize + 2 pad][xsize + 2 pad] or null
+  int pad;
 };
 
 // numerics.hpp:77-89 with every operation explicitly rounded (no FMA contraction)
@@ -87,6 +90,14 @@ __device__ __forceinline__ bool collision_check_pose(const CollisionParams& p, d
   if (j == g.xsize) j--;
   if (i == g.ysize) i--;
   const int cx = (int)j, cy = (int)i;
+  if (p.inflated)
+  {
+    // centres farther than `pad` outside the map cannot reach an in-bounds cell
+    const long long px = (long long)cx + p.pad, py = (long long)cy + p.pad;
+    const long long pw = (long long)g.xsize + 2 * p.pad, ph = (long long)g.ysize + 2 * p.pad;
+    if (px < 0 || py < 0 || px >= pw || py >= ph) return false;
+    return __ldg(p.inflated + (size_t)py * (size_t)pw + (size_t)px) != 0;
+  }
   // Collision::search (:150-167), pruned to the radii that can satisfy sqrd_obs <= r_col^2
   const int r_last = (p.r_col + 1 < kPruneVerified) ? min(p.r_max, p.r_col) : p.r_max;
   for (int r0 = p.r_bnd; r0 <= r_last; r0++)
@@ -114,6 +125,34 @@ __device__ __forceinline__ bool collision_check_pose(const CollisionParams& p, d
     }
   }
   return false;
+}
+
+// Map dilation.  collisionCheck(pose) is the OR, over a FIXED set of cell offsets around the
+// pose's cell (the cells of the circle walks r_bnd .. r_col that satisfy dx^2 + dy^2 <= r_col^2),
+// of "in bounds and occupied" -- the early returns of the reference only shorten the walk.  For
+// workloads that check far more poses than the map has cells (DynamicWindow: 120 rollouts x 20
+// poses per robot) the OR is evaluated once per cell into a padded byte map and every pose
+// check becomes a single lookup; the flags are identical by construction.  offsets: (dj, di).
+__global__ void __launch_bounds__(256) inflate_kernel(const GridView g, double thr, const short2* __restrict__ offsets,
+                                                      int noffsets, int pad, unsigned char* __restrict__ out)
+{
+  const long long pw = (long long)g.xsize + 2 * pad, ph = (long long)g.ysize + 2 * pad;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pw * ph) return;
+  const int cx = (int)(idx % pw) - pad, cy = (int)(idx / pw) - pad;
+  unsigned char hit = 0;
+  for (int o = 0; o < noffsets; o++)
+  {
+    const short2 d = __ldg(offsets + o);
+    const unsigned int cj = (unsigned int)(cx + d.x), ci = (unsigned int)(cy + d.y);
+    if (ci <= g.ysize - 1u && cj <= g.xsize - 1u &&
+        !((double)__ldg(g.data + (size_t)ci * g.xsize + cj) / 100.0 < thr))
+    {
+      hit = 1;
+      break;
+    }
+  }
+  out[idx] = hit;
 }
 
 __global__ void __launch_bounds__(128) collision_check_kernel(const CollisionParams p)

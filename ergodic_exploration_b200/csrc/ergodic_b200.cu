@@ -1282,6 +1282,14 @@ struct eb_grid
   int* d_out = nullptr;
   int cap = 0;
   long long launches = 0;
+  // pre-dilated map for one set of collision radii / threshold (collision_kernels.cuh, inflate_kernel)
+  unsigned char* d_inflated = nullptr;
+  short2* d_offsets = nullptr;
+  bool infl_valid = false;
+  int infl_key[3] = { -1, -1, -1 };  // r_bnd, r_last, r_col
+  double infl_thr = 0.0;
+  int infl_pad = 0;
+  int dilation_mode = 0;  // 0 auto (by pose count), 1 never, 2 always
 };
 
 namespace
@@ -1300,6 +1308,78 @@ eb_status collision_params(const eb_grid* g, const eb_collision* c, eb::Collisio
   p->r_col = (int)std::floor((c->boundary_radius + c->obstacle_threshold) / g->view.resolution);
   p->r_max = (int)std::floor(c->search_radius / g->view.resolution);
   p->occupied_threshold = c->occupied_threshold;
+  return EB_OK;
+}
+
+// Points p at the dilated map of (g, radii, threshold), building it if `build`; with
+// build = false it is used only when it already exists for exactly these parameters.
+eb_status use_inflated(eb_grid* g, eb::CollisionParams* p, bool build)
+{
+  const int r_last = (p->r_col + 1 < eb::kPruneVerified) ? std::min(p->r_max, p->r_col) : p->r_max;
+  const bool match = g->infl_valid && g->infl_key[0] == p->r_bnd && g->infl_key[1] == r_last &&
+                     g->infl_key[2] == p->r_col && g->infl_thr == p->occupied_threshold;
+  if (g->dilation_mode == 1) return EB_OK;
+  if (g->dilation_mode == 2) build = true;
+  if (!match)
+  {
+    if (!build) return EB_OK;
+    if (p->r_col < 0 || p->r_col > 30000) return EB_OK;  // degenerate radii: keep the direct walk
+    // the fixed offset set: cells of the reference's circle walks that can report a collision
+    std::vector<short2> offs;
+    {
+      std::vector<long long> seen;
+      for (int r0 = std::max(p->r_bnd, 0); r0 <= r_last; r0++)
+      {
+        int x = -r0, y = 0, err = 2 - 2 * r0;
+        while (x < 0)
+        {
+          const int q[4][2] = { { -x, y }, { -y, -x }, { x, -y }, { y, x } };
+          for (auto& d : q)
+            if ((long long)d[0] * d[0] + (long long)d[1] * d[1] <= (long long)p->r_col * p->r_col)
+              seen.push_back(((long long)(d[0] + 32768) << 20) | (long long)(d[1] + 32768));
+          const int r = err;
+          if (r <= y)
+          {
+            y++;
+            err += 2 * y + 1;
+          }
+          if (r > x || err > y)
+          {
+            x++;
+            err += 2 * x + 1;
+          }
+        }
+      }
+      std::sort(seen.begin(), seen.end());
+      seen.erase(std::unique(seen.begin(), seen.end()), seen.end());
+      for (long long v : seen) offs.push_back(make_short2((short)((v >> 20) - 32768), (short)((v & 0xfffff) - 32768)));
+    }
+    const int pad = std::max(p->r_col, 0);
+    const size_t pw = (size_t)g->view.xsize + 2 * (size_t)pad, ph = (size_t)g->view.ysize + 2 * (size_t)pad;
+    cudaFree(g->d_inflated);
+    cudaFree(g->d_offsets);
+    g->d_inflated = nullptr;
+    g->d_offsets = nullptr;
+    g->infl_valid = false;
+    EB_CUDA(cudaMalloc(&g->d_inflated, pw * ph));
+    EB_CUDA(cudaMalloc(&g->d_offsets, sizeof(short2) * std::max<size_t>(offs.size(), 1)));
+    EB_CUDA(cudaMemcpyAsync(g->d_offsets, offs.data(), sizeof(short2) * offs.size(), cudaMemcpyHostToDevice, g->stream));
+    EB_CUDA(cudaStreamSynchronize(g->stream));  // offs is a stack-lifetime buffer
+    const size_t total = pw * ph;
+    eb::inflate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g->stream>>>(g->view, p->occupied_threshold,
+                                                                                 g->d_offsets, (int)offs.size(), pad,
+                                                                                 g->d_inflated);
+    EB_CUDA(cudaGetLastError());
+    g->launches += 1;
+    g->infl_key[0] = p->r_bnd;
+    g->infl_key[1] = r_last;
+    g->infl_key[2] = p->r_col;
+    g->infl_thr = p->occupied_threshold;
+    g->infl_pad = pad;
+    g->infl_valid = true;
+  }
+  p->inflated = g->d_inflated;
+  p->pad = g->infl_pad;
   return EB_OK;
 }
 
@@ -1352,6 +1432,7 @@ eb_status eb_grid_update(eb_grid* g, const signed char* data)
   EB_CUDA(cudaSetDevice(g->device));
   EB_CUDA(cudaMemcpyAsync(g->d_data, data, (size_t)g->view.xsize * g->view.ysize, cudaMemcpyHostToDevice, g->stream));
   EB_CUDA(cudaStreamSynchronize(g->stream));
+  g->infl_valid = false;  // the dilated map belongs to the old cells
   return EB_OK;
 }
 
@@ -1360,6 +1441,8 @@ void eb_grid_destroy(eb_grid* g)
   if (!g) return;
   cudaSetDevice(g->device);
   cudaFree(g->d_data);
+  cudaFree(g->d_inflated);
+  cudaFree(g->d_offsets);
   cudaFree(g->d_a);
   cudaFree(g->d_b);
   cudaFree(g->d_out);
@@ -1375,6 +1458,13 @@ eb_status eb_grid_set_stream(eb_grid* g, void* s)
 
 long long eb_grid_launch_count(const eb_grid* g) { return g ? g->launches : 0; }
 
+eb_status eb_grid_set_dilation(eb_grid* g, int mode)
+{
+  if (!g || mode < 0 || mode > 2) return fail(EB_ERR_INVALID_ARGUMENT, "eb_grid_set_dilation: mode must be 0, 1 or 2");
+  g->dilation_mode = mode;
+  return EB_OK;
+}
+
 eb_status eb_collision_check_dev(eb_grid* g, const eb_collision* c, const double* poses_dev, int count, int* hit_dev)
 {
   eb::CollisionParams p{};
@@ -1387,6 +1477,9 @@ eb_status eb_collision_check_dev(eb_grid* g, const eb_collision* c, const double
   p.B = count;
   p.x0 = poses_dev;
   p.out = hit_dev;
+  // a dilated map pays once the poses outnumber a fraction of the cells; an existing one is free
+  st = use_inflated(g, &p, (long long)count * 4 >= (long long)g->view.xsize * g->view.ysize);
+  if (st != EB_OK) return st;
   eb::collision_check_kernel<<<(count + 127) / 128, 128, 0, g->stream>>>(p);
   EB_CUDA(cudaGetLastError());
   g->launches += 1;
@@ -1409,6 +1502,8 @@ eb_status eb_validate_control_dev(eb_grid* g, const eb_collision* c, const doubl
   p.out = valid_dev;
   p.dt = dt;
   p.steps = (int)static_cast<unsigned int>(std::abs(horizon / dt));  // numerics.hpp:316
+  st = use_inflated(g, &p, (long long)count * p.steps * 4 >= (long long)g->view.xsize * g->view.ysize);
+  if (st != EB_OK) return st;
   eb::validate_control_kernel<<<(count + 127) / 128, 128, 0, g->stream>>>(p);
   EB_CUDA(cudaGetLastError());
   g->launches += 1;
@@ -1482,6 +1577,11 @@ eb_status dwa_launch(eb_grid* g, eb::DwaParams& p)
 {
   if (p.B == 0) return EB_OK;
   EB_CUDA(cudaSetDevice(g->device));
+  {
+    const long long poses = (long long)p.B * p.col.steps * p.n[0] * p.n[1] * p.n[2];
+    const eb_status st = use_inflated(g, &p.col, poses * 4 >= (long long)g->view.xsize * g->view.ysize);
+    if (st != EB_OK) return st;
+  }
   const int threads = 128, warps_per_block = threads / 32;
   eb::dwa_control_kernel<<<(p.B + warps_per_block - 1) / warps_per_block, threads, 0, g->stream>>>(p);
   EB_CUDA(cudaGetLastError());

@@ -268,6 +268,11 @@ eb_status eb_validate_control_host(eb_grid *g, const eb_collision *c, const doub
 eb_status eb_validate_control_dev(eb_grid *g, const eb_collision *c, const double *x0_dev, const double *u_dev,
                                   int count, double dt, double horizon, int *valid_dev);
 long long eb_grid_launch_count(const eb_grid *g);
+/* The checks can run against a pre-dilated copy of the map (one lookup per pose instead of the circle
+ * walk; identical flags, built once per map update and set of radii).  mode 0 = automatic (when a call
+ * checks more poses than a quarter of the map's cells, or a matching copy already exists), 1 = never,
+ * 2 = always. */
+eb_status eb_grid_set_dilation(eb_grid *g, int mode);
 
 /* ---- DynamicWindow -----------------------------------
  * Batched DynamicWindow::control (dynamic_window.cpp:93-187): for every instance the

@@ -30,9 +30,10 @@ def test_collision_check_matches_cpu(case):
                              rng.uniform(ymin - 0.7, ymin + ys * res + 0.7, n), rng.uniform(-3.1, 3.1, n)])
     poses[0, :2] = (xmin + xs * res, ymin + ys * res)
     poses[1, :2] = (xmin, ymin)
-    got = c.collisionCheck(grid, poses)
     want = Oracle.collision_check(data, res, xmin, ymin, col, poses)
-    np.testing.assert_array_equal(got, want)
+    for mode in (1, 2, 0):  # circle walk, pre-dilated map, automatic
+        grid.dilation(mode)
+        np.testing.assert_array_equal(c.collisionCheck(grid, poses), want)
     assert 0 < want.sum() < n
 
 
@@ -50,9 +51,10 @@ def test_validate_control_matches_cpu(case):
     u = np.column_stack([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), rng.uniform(-2, 2, n)])
     u[::5, 2] = 0.0
     for dt, horizon in ((0.1, 0.5), (0.1, 2.0), (0.05, 0.33)):
-        got = eb.validate_control(c, grid, x0, u, dt, horizon)
         want = Oracle.validate_control(data, res, xmin, ymin, col, x0, u, dt, horizon)
-        np.testing.assert_array_equal(got, want)
+        for mode in (1, 2):
+            grid.dilation(mode)
+            np.testing.assert_array_equal(eb.validate_control(c, grid, x0, u, dt, horizon), want)
         assert want.sum() < n and (want.sum() > 0 or col[3] == 0.0)  # threshold 0: every known cell is an obstacle
 
 

@@ -30,10 +30,12 @@ def test_dwa_twist_matches_cpu(cfg, samples):
     grid, col = _setup(data, res)
     dwa = eb.DynamicWindow(col, *cfg, *samples)
     cost = np.empty(n)
-    found, u = dwa.control(grid, x0, vb, vref=vref, min_cost=cost)
     fo, uo, co = Oracle.dwa_control(data, res, 0.0, 0.0, COL, cfg, samples, x0, vb, vref=vref)
-    np.testing.assert_array_equal(found, fo)
-    np.testing.assert_array_equal(u, uo)
+    for mode in (1, 2):  # circle walks, pre-dilated map
+        grid.dilation(mode)
+        found, u = dwa.control(grid, x0, vb, vref=vref, min_cost=cost)
+        np.testing.assert_array_equal(found, fo)
+        np.testing.assert_array_equal(u, uo)
     assert_abs_rel_close(cost[fo == 1], co[fo == 1], "min cost")
     assert 0 < fo.sum()
 
