@@ -143,6 +143,19 @@ class ErgodicControl:
         other._h = h
         return other
 
+    def _host_ptr(self, a: np.ndarray) -> int:
+        """data pointer of a host array; a control loop passes the same buffers every tick, so the
+        last few (array, pointer) pairs are remembered (holding the array keeps its id unique)"""
+        cache = self.__dict__.setdefault("_ptrs", {})
+        hit = cache.get(id(a))
+        if hit is not None and hit[0] is a:
+            return hit[1]
+        if len(cache) >= 8:
+            cache.clear()
+        ptr = a.ctypes.data
+        cache[id(a)] = (a, ptr)
+        return ptr
+
     def _sync_stream(self):
         if torch is not None and torch.cuda.is_available():
             s = torch.cuda.current_stream(self.device).cuda_stream
@@ -178,8 +191,8 @@ class ErgodicControl:
         """One control() iteration for all instances.  Returns u0 (B, 3); pass
         ``metric`` (B,) to also receive sum_k lamda_k (c_k - phi_k)^2."""
         b = grid.as_tuple() if hasattr(grid, "as_tuple") else tuple(float(v) for v in grid)
-        self._sync_stream()
         if _is_cuda_tensor(x):
+            self._sync_stream()  # device path: run on torch's current stream
             assert x.dtype == torch.float64 and x.is_contiguous() and x.numel() == 3 * self.batch
             if u0 is None:
                 u0 = torch.empty((self.batch, 3), dtype=torch.float64, device=x.device)
@@ -188,15 +201,18 @@ class ErgodicControl:
             st = self._lib.eb_control_dev(self._h, *b, C.c_void_p(x.data_ptr()), idx_p,
                                           C.c_void_p(u0.data_ptr()), met_p)
         else:
-            x = _np_f64(x).reshape(self.batch, 3)
+            # host path: the call copies / maps the buffers and synchronises by itself
+            if not (type(x) is np.ndarray and x.dtype == np.float64 and x.flags.c_contiguous
+                    and x.size == 3 * self.batch):
+                x = _np_f64(x).reshape(self.batch, 3)
             if u0 is None:
                 u0 = np.empty((self.batch, 3))
             idx_p = None
             if mem_idx is not None:
                 mem_idx = np.ascontiguousarray(mem_idx, dtype=np.int32)
                 idx_p = mem_idx.ctypes.data
-            met_p = metric.ctypes.data if metric is not None else None
-            st = self._lib.eb_control_host(self._h, *b, x.ctypes.data, idx_p, u0.ctypes.data, met_p)
+            met_p = self._host_ptr(metric) if metric is not None else None
+            st = self._lib.eb_control_host(self._h, *b, self._host_ptr(x), idx_p, self._host_ptr(u0), met_p)
         if st == capi.EB_ERR_INVALID_ARGUMENT:
             raise ValueError(self._lib.eb_last_error().decode())
         check(st)

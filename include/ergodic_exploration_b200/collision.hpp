@@ -8,6 +8,7 @@
  * after ErgodicControl::control() on every tick (exploration.hpp:238):
  *   Collision::collisionCheck(grid, pose)                     collision.cpp:126-143
  *   validate_control(collision, grid, x0, u, dt, horizon)     numerics.hpp:312-330
+ *   DynamicWindow::control(grid, x0, vb, vref | xt_ref)       dynamic_window.cpp:93-187
  * for one pose / twist (the reference's signatures) or for a 3 x B batch sharing one map.
  * The grid type is anything with the reference GridMap's getters
  * (gridData(), xsize(), ysize(), resolution(), xmin(), ymin(); grid.hpp:201-255).
@@ -19,7 +20,9 @@
 #define ERGODIC_EXPLORATION_B200_COLLISION_HPP
 
 #include <memory>
+#include <cmath>
 #include <stdexcept>
+#include <tuple>
 #include <vector>
 
 #include <armadillo>
@@ -126,6 +129,68 @@ inline std::vector<int> validate_control(const Collision& collision, const Devic
                                  static_cast<int>(x0.n_cols), dt, horizon, valid.data()));
   return valid;
 }
+/** @brief DynamicWindow (dynamic_window.hpp:60-172) evaluated on the GPU, one robot or a batch */
+class DynamicWindow
+{
+public:
+  /** @brief same argument order as dynamic_window.hpp:60-65 */
+  DynamicWindow(const Collision& collision, double dt, double horizon, double acc_dt, double acc_lim_x,
+                double acc_lim_y, double acc_lim_th, double max_vel_x, double min_vel_x, double max_vel_y,
+                double min_vel_y, double max_rot_vel, double min_rot_vel, unsigned int vx_samples,
+                unsigned int vy_samples, unsigned int vth_samples)
+    : collision_(collision)
+    , cfg_{ dt,        horizon,   acc_dt,    acc_lim_x,   acc_lim_y,   acc_lim_th, max_vel_x,  min_vel_x,
+            max_vel_y, min_vel_y, max_rot_vel, min_rot_vel, vx_samples, vy_samples, vth_samples }
+  {
+  }
+
+  /** @brief dynamic_window.cpp:93-139: (collision-free twist found, optimal twist) */
+  std::tuple<bool, arma::vec> control(const DeviceGrid& grid, const arma::vec& x0, const arma::vec& vb,
+                                      const arma::vec& vref) const
+  {
+    if (x0.n_elem != 3 || vb.n_elem != 3 || vref.n_elem != 3) throw std::logic_error("DynamicWindow::control: 3-vectors");
+    int found = 0;
+    arma::vec u(3);
+    check(eb_dwa_control_twist_host(grid.handle(), &collision_.config(), &cfg_, x0.memptr(), vb.memptr(),
+                                    vref.memptr(), 1, &found, u.memptr(), nullptr));
+    return std::make_tuple(found != 0, u);
+  }
+
+  /** @brief dynamic_window.cpp:141-187: follow a reference trajectory (3 x n, time step dt_ref) */
+  std::tuple<bool, arma::vec> control(const DeviceGrid& grid, const arma::vec& x0, const arma::vec& vb,
+                                      const arma::mat& xt_ref, double dt_ref) const
+  {
+    if (x0.n_elem != 3 || vb.n_elem != 3 || xt_ref.n_rows != 3 || xt_ref.n_cols < 1)
+      throw std::logic_error("DynamicWindow::control: x0, vb 3-vectors and xt_ref 3 x n");
+    int found = 0;
+    arma::vec u(3);
+    check(eb_dwa_control_traj_host(grid.handle(), &collision_.config(), &cfg_, x0.memptr(), vb.memptr(),
+                                   xt_ref.memptr(), static_cast<int>(xt_ref.n_cols), 0, dt_ref, 1, &found, u.memptr(),
+                                   nullptr));
+    return std::make_tuple(found != 0, u);
+  }
+
+  /** @brief batch: x0, vb, vref are 3 x B; returns the B found flags and the 3 x B optimal twists */
+  std::tuple<std::vector<int>, arma::mat> controlBatch(const DeviceGrid& grid, const arma::mat& x0, const arma::mat& vb,
+                                                      const arma::mat& vref) const
+  {
+    if (x0.n_rows != 3 || vb.n_rows != 3 || vref.n_rows != 3 || x0.n_cols != vb.n_cols || x0.n_cols != vref.n_cols)
+      throw std::logic_error("DynamicWindow::controlBatch: x0, vb, vref must be 3 x B");
+    std::vector<int> found(x0.n_cols);
+    arma::mat u(3, x0.n_cols);
+    check(eb_dwa_control_twist_host(grid.handle(), &collision_.config(), &cfg_, x0.memptr(), vb.memptr(),
+                                    vref.memptr(), static_cast<int>(x0.n_cols), found.data(), u.memptr(), nullptr));
+    return std::make_tuple(found, u);
+  }
+
+  double timeStep() const { return cfg_.dt; }
+  double horizon() const { return cfg_.horizon; }
+  unsigned int steps() const { return static_cast<unsigned int>(std::abs(cfg_.horizon / cfg_.dt)); }
+
+private:
+  Collision collision_;
+  eb_dwa cfg_;
+};
 }  // namespace b200
 }  // namespace ergodic_exploration
 #endif

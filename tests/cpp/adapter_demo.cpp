@@ -251,6 +251,20 @@ static int run_gpu(const ModelT& model, const mat& Rinv, const vec& umin, const 
     std::vector<double> hd(hit.begin(), hit.end()), vd(valid.begin(), valid.end());
     print_vec("chit", hd.data(), hd.size());
     print_vec("cvalid", vd.data(), vd.size());
+    // DynamicWindow (exploration_omni_node.cpp:204-206), one robot and the batch
+    const b200::DynamicWindow dwa(col, 0.1, 2.0, 0.2, 2.5, 2.5, 1.0, 1.0, -1.0, 1.0, -1.0, 2.0, -2.0, 3, 8, 5);
+    REQUIRE(dwa.steps() == 20);
+    mat vref(3, B, arma::fill::zeros);
+    const auto [dfound, dtw] = dwa.controlBatch(dgrid, p0, tw, vref);
+    const auto [f7, u7] = dwa.control(dgrid, vec(p0.col(7)), vec(tw.col(7)), vec(vref.col(7)));
+    REQUIRE(f7 == (dfound[7] != 0) && u7(0) == dtw(0, 7) && u7(1) == dtw(1, 7) && u7(2) == dtw(2, 7));
+    const auto [f9, u9] = dwa.control(dgrid, vec(p0.col(9)), vec(tw.col(9)), p0, 0.1);  // any 3 x n path will do
+    std::vector<double> fd(dfound.begin(), dfound.end());
+    print_vec("dfound", fd.data(), fd.size());
+    print_vec("dtwist", dtw.memptr(), dtw.n_elem);
+    const double f9d = f9 ? 1.0 : 0.0;
+    print_vec("dtraj", &f9d, 1);
+    print_vec("dtraju", u9.memptr(), 3);
   }
   std::printf("OK\n");
   return 0;

@@ -92,3 +92,11 @@ def test_adapter_closed_loop_matches_oracle(demo, model):
     np.testing.assert_array_equal(rec["cvalid"][0].astype(int),
                                   Oracle.validate_control(data, 0.05, -1.0, 0.5, col, poses, twists, 0.1, 1.0))
     assert 0 < rec["cvalid"][0].sum() < len(poses)
+    dwa_cfg = (0.1, 2.0, 0.2, 2.5, 2.5, 1.0, 1.0, -1.0, 1.0, -1.0, 2.0, -2.0)
+    fo, uo, _ = Oracle.dwa_control(data, 0.05, -1.0, 0.5, col, dwa_cfg, (3, 8, 5), poses, twists, vref=np.zeros_like(twists))
+    np.testing.assert_array_equal(rec["dfound"][0].astype(int), fo)
+    np.testing.assert_array_equal(rec["dtwist"][0].reshape(-1, 3), uo)
+    ft, ut, _ = Oracle.dwa_control(data, 0.05, -1.0, 0.5, col, dwa_cfg, (3, 8, 5), poses[9:10], twists[9:10], xt_ref=poses,
+                                   dt_ref=0.1)
+    assert int(rec["dtraj"][0][0]) == ft[0]
+    np.testing.assert_array_equal(rec["dtraju"][0], ut[0])

@@ -6,7 +6,7 @@ python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 python tools/benchline.py < gpurun_out/bench_default.json
-for w in c5 c4 c3 c2big; do
+for w in c5 c4 c3 c2big collide dwa; do
   python bench.py --workload $w --steps 30 --warmup 5 > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
   python tools/benchline.py < gpurun_out/bench_$w.json
 done
