@@ -155,6 +155,38 @@ __global__ void __launch_bounds__(256) inflate_kernel(const GridView g, double t
   out[idx] = hit;
 }
 
+// The same map, built the other way round: every OCCUPIED in-bounds cell marks the centres
+// that can see it (centre = cell - offset).  Occupied cells are a small fraction of a map, so
+// this touches far fewer bytes than the per-centre gather above; `out` must be zeroed first.
+// The stores race only with stores of the same value.
+__global__ void __launch_bounds__(256) inflate_scatter_kernel(const GridView g, double thr,
+                                                              const short2* __restrict__ offsets, int noffsets,
+                                                              int pad, unsigned char* __restrict__ out)
+{
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)g.xsize * g.ysize) return;
+  if ((double)__ldg(g.data + idx) / 100.0 < thr) return;
+  const int cj = (int)(idx % g.xsize), ci = (int)(idx / g.xsize);
+  const long long pw = (long long)g.xsize + 2 * pad;
+  for (int o = 0; o < noffsets; o++)
+  {
+    const short2 d = __ldg(offsets + o);
+    // centre (cj - dx, ci - dy) always lies inside the padded map: |d| <= r_col = pad
+    out[(size_t)(ci - d.y + pad) * (size_t)pw + (size_t)(cj - d.x + pad)] = 1;
+  }
+}
+
+// fraction of occupied cells, to pick between the two builders
+__global__ void __launch_bounds__(256) count_occupied_kernel(const GridView g, double thr, unsigned long long* count)
+{
+  const long long n = (long long)g.xsize * g.ysize;
+  unsigned int local = 0;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+    local += !((double)__ldg(g.data + idx) / 100.0 < thr);
+  local = __reduce_add_sync(kFull, local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
+}
+
 __global__ void __launch_bounds__(128) collision_check_kernel(const CollisionParams p)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1279,6 +1279,10 @@ struct eb_grid
   cudaStream_t stream = nullptr;
   double* d_a = nullptr;  // staging for the _host calls: poses / x0
   double* d_b = nullptr;  // twists
+  double* d_u = nullptr;  // DynamicWindow: optimal twists
+  double* d_cost = nullptr;
+  double* d_ref = nullptr;  // DynamicWindow: reference twists / trajectories
+  size_t ref_cap = 0;
   int* d_out = nullptr;
   int cap = 0;
   long long launches = 0;
@@ -1366,11 +1370,33 @@ eb_status use_inflated(eb_grid* g, eb::CollisionParams* p, bool build)
     EB_CUDA(cudaMemcpyAsync(g->d_offsets, offs.data(), sizeof(short2) * offs.size(), cudaMemcpyHostToDevice, g->stream));
     EB_CUDA(cudaStreamSynchronize(g->stream));  // offs is a stack-lifetime buffer
     const size_t total = pw * ph;
-    eb::inflate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g->stream>>>(g->view, p->occupied_threshold,
-                                                                                 g->d_offsets, (int)offs.size(), pad,
-                                                                                 g->d_inflated);
+    // gather per centre, or scatter from the occupied cells when they are few (the usual case)
+    unsigned long long* d_count = nullptr;
+    unsigned long long occupied = 0;
+    const size_t cells = (size_t)g->view.xsize * g->view.ysize;
+    EB_CUDA(cudaMalloc(&d_count, sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), g->stream);
+    if (e == cudaSuccess)
+    {
+      eb::count_occupied_kernel<<<(unsigned)std::min<size_t>((cells + 255) / 256, 4096), 256, 0, g->stream>>>(
+          g->view, p->occupied_threshold, d_count);
+      e = cudaMemcpyAsync(&occupied, d_count, sizeof(occupied), cudaMemcpyDeviceToHost, g->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+    cudaFree(d_count);
+    if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("dilated map: ") + cudaGetErrorString(e));
+    if (occupied * 4 <= cells)
+    {
+      EB_CUDA(cudaMemsetAsync(g->d_inflated, 0, total, g->stream));
+      eb::inflate_scatter_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, g->stream>>>(
+          g->view, p->occupied_threshold, g->d_offsets, (int)offs.size(), pad, g->d_inflated);
+    }
+    else
+      eb::inflate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g->stream>>>(g->view, p->occupied_threshold,
+                                                                                   g->d_offsets, (int)offs.size(), pad,
+                                                                                   g->d_inflated);
     EB_CUDA(cudaGetLastError());
-    g->launches += 1;
+    g->launches += 2;
     g->infl_key[0] = p->r_bnd;
     g->infl_key[1] = r_last;
     g->infl_key[2] = p->r_col;
@@ -1388,12 +1414,16 @@ eb_status grid_reserve(eb_grid* g, int count)
   if (count <= g->cap) return EB_OK;
   cudaFree(g->d_a);
   cudaFree(g->d_b);
+  cudaFree(g->d_u);
+  cudaFree(g->d_cost);
   cudaFree(g->d_out);
-  g->d_a = g->d_b = nullptr;
+  g->d_a = g->d_b = g->d_u = g->d_cost = nullptr;
   g->d_out = nullptr;
   g->cap = 0;
   EB_CUDA(cudaMalloc(&g->d_a, sizeof(double) * 3 * (size_t)count));
   EB_CUDA(cudaMalloc(&g->d_b, sizeof(double) * 3 * (size_t)count));
+  EB_CUDA(cudaMalloc(&g->d_u, sizeof(double) * 3 * (size_t)count));
+  EB_CUDA(cudaMalloc(&g->d_cost, sizeof(double) * (size_t)count));
   EB_CUDA(cudaMalloc(&g->d_out, sizeof(int) * (size_t)count));
   g->cap = count;
   return EB_OK;
@@ -1445,6 +1475,9 @@ void eb_grid_destroy(eb_grid* g)
   cudaFree(g->d_offsets);
   cudaFree(g->d_a);
   cudaFree(g->d_b);
+  cudaFree(g->d_u);
+  cudaFree(g->d_cost);
+  cudaFree(g->d_ref);
   cudaFree(g->d_out);
   delete g;
 }
@@ -1640,33 +1673,32 @@ static eb_status dwa_host(eb_grid* g, const eb_collision* c, const eb_dwa* d, co
     return fail(EB_ERR_INVALID_ARGUMENT, "eb_dwa_control_host: bad arguments");
   if (count == 0) return EB_OK;
   EB_CUDA(cudaSetDevice(g->device));
-  DevBuf dx, dv, dr, du, dc;
-  int* dfound = nullptr;
-  EB_CUDA(dx.alloc(3 * (size_t)count));
-  EB_CUDA(dv.alloc(3 * (size_t)count));
-  EB_CUDA(dr.alloc(ref_doubles));
-  EB_CUDA(du.alloc(3 * (size_t)count));
-  EB_CUDA(dc.alloc((size_t)count));
-  EB_CUDA(cudaMalloc(&dfound, sizeof(int) * (size_t)count));
-  auto done = [&](eb_status st) {
-    cudaFree(dfound);
-    return st;
-  };
-  cudaError_t e = cudaMemcpyAsync(dx.p, x0, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dv.p, vb, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dr.p, ref, sizeof(double) * ref_doubles, cudaMemcpyHostToDevice, g->stream);
-  if (e != cudaSuccess) return done(fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e)));
-  eb_status st = traj ? eb_dwa_control_traj_dev(g, c, d, dx.p, dv.p, dr.p, ncols, per_instance, dt_ref, count, dfound,
-                                                du.p, dc.p) :
-                        eb_dwa_control_twist_dev(g, c, d, dx.p, dv.p, dr.p, count, dfound, du.p, dc.p);
-  if (st != EB_OK) return done(st);
-  e = cudaMemcpyAsync(found, dfound, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(u_opt, du.p, sizeof(double) * 3 * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
+  // staging buffers live with the grid (grown on demand), so a control loop pays no allocation per tick
+  eb_status st = grid_reserve(g, count);
+  if (st != EB_OK) return st;
+  if (ref_doubles > g->ref_cap)
+  {
+    cudaFree(g->d_ref);
+    g->d_ref = nullptr;
+    g->ref_cap = 0;
+    EB_CUDA(cudaMalloc(&g->d_ref, sizeof(double) * ref_doubles));
+    g->ref_cap = ref_doubles;
+  }
+  cudaError_t e = cudaMemcpyAsync(g->d_a, x0, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_b, vb, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_ref, ref, sizeof(double) * ref_doubles, cudaMemcpyHostToDevice, g->stream);
+  if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e));
+  st = traj ? eb_dwa_control_traj_dev(g, c, d, g->d_a, g->d_b, g->d_ref, ncols, per_instance, dt_ref, count, g->d_out,
+                                      g->d_u, g->d_cost) :
+              eb_dwa_control_twist_dev(g, c, d, g->d_a, g->d_b, g->d_ref, count, g->d_out, g->d_u, g->d_cost);
+  if (st != EB_OK) return st;
+  e = cudaMemcpyAsync(found, g->d_out, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(u_opt, g->d_u, sizeof(double) * 3 * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
   if (e == cudaSuccess && min_cost)
-    e = cudaMemcpyAsync(min_cost, dc.p, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
+    e = cudaMemcpyAsync(min_cost, g->d_cost, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
-  if (e != cudaSuccess) return done(fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e)));
-  return done(EB_OK);
+  if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e));
+  return EB_OK;
 }
 
 eb_status eb_dwa_control_twist_host(eb_grid* g, const eb_collision* c, const eb_dwa* d, const double* x0,
