@@ -1119,6 +1119,12 @@ struct eb_peer_group
   unsigned long long* peer_flags[eb::kMaxPeers] = {};
   bool connected = false;
   unsigned long long step = 0;                  // steps launched so far
+  // side-stream publication (small batches): rotating local u0 blocks, the group's own stream and events
+  double* local_u0[eb::kPeerBuffers] = {};
+  cudaStream_t side = nullptr;
+  cudaEvent_t solved[eb::kPeerBuffers] = {}, published[eb::kPeerBuffers] = {};
+  unsigned int* side_counter = nullptr;
+  int fuse_min_batch = 32768;                   // batches at least this large publish from inside the solve kernel
 };
 
 extern "C" {
@@ -1147,6 +1153,16 @@ eb_status eb_peer_group_create(int device, int rank, int world, long long elems_
   }
   if (e == cudaSuccess) e = cudaMalloc(&g->flags, sizeof(unsigned long long) * eb::kMaxPeers);
   if (e == cudaSuccess) e = cudaMalloc(&g->counter, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&g->side_counter, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(g->side_counter, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking);
+  for (int k = 0; k < eb::kPeerBuffers && e == cudaSuccess; k++)
+  {
+    e = cudaMalloc(&g->local_u0[k], sizeof(double) * (size_t)elems_per_rank);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->solved[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->published[k], cudaEventDisableTiming);
+  }
+  if (const char* env = std::getenv("EB_GATHER_FUSE_MIN_BATCH")) g->fuse_min_batch = std::atoi(env);
   if (e == cudaSuccess) e = cudaMemset(g->flags, 0, sizeof(unsigned long long) * eb::kMaxPeers);
   if (e == cudaSuccess) e = cudaMemset(g->counter, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -1212,7 +1228,16 @@ void eb_peer_group_destroy(eb_peer_group* g)
         for (int k = 0; k < eb::kPeerBuffers; k++) cudaIpcCloseMemHandle(g->peer_gathered[r][k]);
         cudaIpcCloseMemHandle(g->peer_flags[r]);
       }
-  for (int k = 0; k < eb::kPeerBuffers; k++) cudaFree(g->gathered[k]);
+  if (g->side) cudaStreamSynchronize(g->side);
+  for (int k = 0; k < eb::kPeerBuffers; k++)
+  {
+    cudaFree(g->gathered[k]);
+    cudaFree(g->local_u0[k]);
+    if (g->solved[k]) cudaEventDestroy(g->solved[k]);
+    if (g->published[k]) cudaEventDestroy(g->published[k]);
+  }
+  if (g->side) cudaStreamDestroy(g->side);
+  cudaFree(g->side_counter);
   cudaFree(g->flags);
   cudaFree(g->counter);
   delete g;
@@ -1234,8 +1259,43 @@ eb_status eb_control_dev_gather(eb_controller* c, eb_peer_group* g, double xmin,
   if (!c || !g) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather: NULL argument");
   if (!g->connected) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather: peer group is not connected");
   if (g->elems != 3LL * c->B) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather: peer group sized for another batch");
-  PeerLaunch pl;
   const int parity = (int)(g->step % eb::kPeerBuffers);
+  // launching step n + 1 = g->step + 1 into the buffer of step n + 1 - kPeerBuffers: every rank must
+  // have finished step n + 2 - kPeerBuffers (its reads of the older step precede that launch)
+  const unsigned long long need =
+      g->step + 2 > (unsigned long long)eb::kPeerBuffers ? g->step + 2 - eb::kPeerBuffers : 0;
+  if (c->B < g->fuse_min_batch)
+  {
+    // single-wave batch: solve locally, publish from the group's own stream under the next step
+    EB_CUDA(cudaSetDevice(g->device));
+    if (g->step >= (unsigned long long)eb::kPeerBuffers) EB_CUDA(cudaStreamWaitEvent(c->stream, g->published[parity], 0));
+    const eb_status st =
+        eb_control_dev(c, xmin, xmax, ymin, ymax, x_dev, mem_idx_dev, g->local_u0[parity], metric_dev);
+    if (st != EB_OK) return st;
+    EB_CUDA(cudaEventRecord(g->solved[parity], c->stream));
+    EB_CUDA(cudaStreamWaitEvent(g->side, g->solved[parity], 0));
+    eb::PublishParams pp{};
+    pp.src = g->local_u0[parity];
+    pp.elems = g->elems;
+    pp.n_peer = g->world;
+    for (int r = 0; r < g->world; r++)
+    {
+      pp.dst[r] = g->peer_gathered[r][parity] + (size_t)g->rank * (size_t)g->elems;
+      pp.flag[r] = g->peer_flags[r] + g->rank;
+    }
+    pp.flag_value = g->step + 1;
+    pp.my_flags = g->flags;
+    pp.need = need;
+    pp.done_counter = g->side_counter;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(32, (g->elems / 2 + 255) / 256));
+    eb::peer_publish_kernel<<<blocks, 256, 0, g->side>>>(pp);
+    EB_CUDA(cudaGetLastError());
+    EB_CUDA(cudaEventRecord(g->published[parity], g->side));
+    c->launches += 1;
+    g->step += 1;
+    return EB_OK;
+  }
+  PeerLaunch pl;
   pl.n_peer = g->world;
   for (int r = 0; r < g->world; r++)
   {
@@ -1245,9 +1305,7 @@ eb_status eb_control_dev_gather(eb_controller* c, eb_peer_group* g, double xmin,
   pl.flag_value = g->step + 1;
   pl.done_counter = g->counter;
   pl.my_flags = g->flags;
-  // launching step n + 1 = g->step + 1 into the buffer of step n + 1 - kPeerBuffers: every rank must
-  // have finished step n + 2 - kPeerBuffers (its reads of the older step precede that launch)
-  pl.need = g->step + 2 > (unsigned long long)eb::kPeerBuffers ? g->step + 2 - eb::kPeerBuffers : 0;
+  pl.need = need;
   c->peer = &pl;
   const eb_status st = eb_control_dev(c, xmin, xmax, ymin, ymax, x_dev, mem_idx_dev, c->d_u0, metric_dev);
   c->peer = nullptr;

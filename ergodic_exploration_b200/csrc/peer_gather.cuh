@@ -15,12 +15,64 @@
 // the step after that one -- a rank reads a step's rows before launching its next step, so
 // nobody can still be reading.  In a balanced run that condition is long true: the steps
 // of different ranks are not coupled and no wait kernel sits between launches.
+//
+// Two ways to publish, chosen by batch size (eb_control_dev_gather):
+//  * fused: the solve kernel stores its rows itself (above).  With many waves per SM the
+//    stores and fences of finished warps overlap the math of the others (+2.5 % at 65 536
+//    instances per GPU).
+//  * side stream: a batch that is a single wave (4096 instances: a 31 us kernel) has nothing
+//    to overlap with -- the NVLink round trips of the publication would sit at the kernel's
+//    tail (+34 us at 8 GPUs).  There the solve kernel writes u0 locally and
+//    peer_publish_kernel, on the group's own stream, copies the block to every rank and raises
+//    the flags while the next step's solve kernel already runs.
 #pragma once
 
 #include <cuda_runtime.h>
 
 namespace eb
 {
+constexpr int kPublishPeers = 8;
+
+struct PublishParams
+{
+  const double* src;                          // this rank's first twists of the step, [elems]
+  long long elems;
+  int n_peer;
+  double* dst[kPublishPeers];                 // every rank's gathered buffer, offset to this rank's block
+  unsigned long long* flag[kPublishPeers];    // this rank's slot in every rank's arrival flags
+  unsigned long long flag_value;
+  const unsigned long long* my_flags;         // reuse guard (see solve_kernel.cuh)
+  unsigned long long need;
+  unsigned int* done_counter;
+};
+
+__global__ void __launch_bounds__(256) peer_publish_kernel(const PublishParams p)
+{
+  if (threadIdx.x < p.n_peer)
+    while (*(const volatile unsigned long long*)(p.my_flags + threadIdx.x) < p.need) __nanosleep(100);
+  __syncthreads();
+  const long long pairs = p.elems >> 1;  // elems = 3 * batch; 16-byte pieces, a possible odd tail below
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (long long)gridDim.x * blockDim.x)
+  {
+    const double2 v = reinterpret_cast<const double2*>(p.src)[i];
+    for (int q = 0; q < p.n_peer; q++) reinterpret_cast<double2*>(p.dst[q])[i] = v;
+  }
+  if ((p.elems & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+    for (int q = 0; q < p.n_peer; q++) p.dst[q][p.elems - 1] = p.src[p.elems - 1];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const unsigned int prev = atomicAdd(p.done_counter, 1u);
+    if (prev == gridDim.x - 1)
+    {
+      *p.done_counter = 0u;
+      __threadfence_system();
+      for (int q = 0; q < p.n_peer; q++) *(volatile unsigned long long*)p.flag[q] = p.flag_value;
+    }
+  }
+}
+
 // spins (one thread) until every rank's arrival flag has reached `step`
 __global__ void peer_wait_kernel(const volatile unsigned long long* flags, int world, unsigned long long step)
 {

@@ -15,8 +15,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_single_rank_group_matches_plain_control():
+@pytest.mark.parametrize("fuse_min_batch", ["0", "1000000"])  # publish from inside the kernel / from the side stream
+def test_single_rank_group_matches_plain_control(fuse_min_batch, monkeypatch):
     import torch
+
+    monkeypatch.setenv("EB_GATHER_FUSE_MIN_BATCH", fuse_min_batch)
 
     from ergodic_exploration_b200.sharding import PeerGather
 
@@ -73,7 +76,8 @@ print("PEER_OK", rank)
 """
 
 
-def test_two_ranks_over_nvlink(tmp_path):
+@pytest.mark.parametrize("fuse_min_batch", ["0", "1000000"])
+def test_two_ranks_over_nvlink(tmp_path, fuse_min_batch):
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -82,5 +86,6 @@ def test_two_ranks_over_nvlink(tmp_path):
     script.write_text(WORKER)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT],
-                       capture_output=True, text=True, timeout=300)
+                       capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, EB_GATHER_FUSE_MIN_BATCH=fuse_min_batch))
     assert r.returncode == 0 and r.stdout.count("PEER_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
