@@ -199,7 +199,7 @@ def cpu_reference_rate(wl, sample, steps, warmup, threads=None):
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
-    sample = min(wl["batch"], 4096)
+    sample = min(wl["batch"], args.ref_sample)
     r = cpu_reference_rate(wl, sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "ergodic control solves/sec (batched)", "value": r["value"],
@@ -434,6 +434,111 @@ def run_ours(args, wl, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_loop(args, rank, world, local_rank):
+    """configs[4]: the full receding-horizon loop -- per step addStateMemory(x), control(), and the plant
+    x <- integrate_twist(x, u0, 0.1) with the angle wrap (the reference's own constant-twist integrator;
+    SURVEY section 8d) -- 65536 Omni instances per GPU, 16x16 basis, replay batch 100 drawn by the on-device
+    sampler once more than 100 states are stored.  Everything stays on the device; one event pair
+    brackets the whole loop.  N > 1: every rank loops over its own instances, the first twists of every
+    step are published to all ranks (fused gather) and each rank waits for the complete step."""
+    import torch
+    import torch.distributed as dist
+
+    import ergodic_exploration_b200 as eb
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS["c5"]
+    B, steps, warm = wl["batch"], args.steps, max(3, args.warmup)
+    R, umin, umax = model_params(wl["model"])
+    N, K = int(abs(wl["horizon"] / DT)), wl["nb"] ** 2
+    x, ut, _ = synth_inputs(dict(wl, mem=0), B, seed=0xE16C0D1C + 5 + rank)
+    ctl = eb.ErgodicControl(wl["model"], DT, wl["horizon"], 0.1, 1.0, wl["nb"], steps + warm + 8, 100, R, umin, umax,
+                            batch=B, device=local_rank)
+    ctl.setTarget([eb.Gaussian(m, s) for m, s in zip(MU, SIGMA)])
+    ctl.set_ut(ut)
+    ctl.keep_ck(False)
+    xd = torch.from_numpy(x).to(dev)
+    u0d = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    metd = torch.empty(B, dtype=torch.float64, device=dev)
+    pg = None
+    if world > 1:
+        from ergodic_exploration_b200.sharding import PeerGather
+        pg = PeerGather(ctl)
+
+    def tick():
+        ctl.addStateMemory(xd)  # exploration.hpp:209
+        if pg is not None:
+            step = pg.control(BOUNDS, xd, metric=metd)
+            pg.wait(step)
+            mine = pg.gathered(step)[rank * B:(rank + 1) * B]
+            eb.integrate_twist(xd, mine, DT, out=xd)
+        else:
+            ctl.control(BOUNDS, xd, u0=u0d, metric=metd)
+            eb.integrate_twist(xd, u0d, DT, out=xd)
+
+    for _ in range(warm):
+        tick()
+    ctl.check()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = ctl.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        tick()
+    b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_ms = a.elapsed_time(b)
+    launches = ctl.launch_count() - l0 + steps  # + one integrate_twist kernel per step
+    ctl.check()
+    clk = clocks.stop() if rank == 0 else None
+    metric_now = float(metd.mean())
+    inside = bool(((xd[:, 0] > -1) & (xd[:, 0] < 11) & (xd[:, 1] > -1) & (xd[:, 1] < 11)).all())
+    if pg is not None:
+        pg.close()
+    if world > 1:
+        t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = t.item()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    dfma, dmma = eb.fp64_peak(local_rank)
+    peak = max(dfma, dmma)
+    # replay states per solve: all stored (<= 100) early on, 100 sampled afterwards
+    m_avg = sum(min(warm + i + 1, 100) for i in range(steps)) / steps
+    F = flops_per_solve(K, N, m_avg)
+    line = {
+        "metric": "ergodic control solves/sec (batched)", "value": world * B * steps / (t_ms * 1e-3), "unit": "solves/s",
+        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": t_ms / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"configs[4]: full receding-horizon loop, {steps} control steps, {B} Omni instances per GPU, "
+                               "16x16 basis, replay batch 100 (device sampler), plant = integrate_twist",
+                   "l2": "closed loop, no flush: per-step working set (2 x 157 MB of ut_) exceeds L2",
+                   "timing": "one CUDA-event pair around the whole loop, max over ranks",
+                   "mean_ergodic_metric_at_end": metric_now, "robots_inside_map": inside,
+                   "parallelism": (f"instances sharded over {world} GPUs; u0 of every step published to all ranks by "
+                                   "the solve kernel, each rank waits for the complete step") if world > 1 else "single GPU"},
+        "gpu_launches": int(launches), "clocks": clk,
+        "e2e": None,
+        "roofline": {"kernel": "solve_kernel", "bound": "fp64", "achieved": F * B * steps / (t_ms * 1e-3) / 1e12,
+                     "peak": peak, "unit": "TFLOP/s", "frac": F * B * steps / (t_ms * 1e-3) / 1e12 / peak, "traffic": None,
+                     "flops_per_solve": F, "note": "whole loop (addStateMemory copy + solve + plant), not the kernel alone",
+                     "peak_source": f"measured live by eb_fp64_peak (DFMA {dfma:.2f}, DMMA {dmma:.2f} TFLOP/s)"},
+    }
+    print(json.dumps(line), flush=True)
 
 
 def run_phik(args, rank, world, local_rank):
@@ -740,7 +845,8 @@ def main():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "collide", "dwa"])
+    ap.add_argument("--ref-sample", type=int, default=4096, help="instances per step of the CPU reference arm")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "c5loop", "collide", "dwa"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -749,6 +855,8 @@ def main():
         return run_phik(args, rank, world, local_rank)
     if args.workload in ("collide", "dwa"):
         return run_avoid(args, rank, world, local_rank)
+    if args.workload == "c5loop":
+        return run_loop(args, rank, world, local_rank)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl, rank, world)

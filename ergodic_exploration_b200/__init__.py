@@ -9,12 +9,12 @@ adapter is include/ergodic_exploration_b200/.  No CPU fallback exists.
 """
 from .capi import (EB_ERR_CUDA, EB_ERR_INVALID_ARGUMENT, EB_ERR_NO_DEVICE, EB_OK, MODEL_OMNI,
                    MODEL_SIMPLE_CART, ErgodicB200Error)
-from .collision import Collision, DynamicWindow, GridMap, validate_control
+from .collision import Collision, DynamicWindow, GridMap, integrate_twist, validate_control
 from .controller import (ErgodicControl, Gaussian, GridBounds, Omni, PhikPlan, SimpleCart, Target,
                          fp64_peak)
 
 __all__ = [
-    "Collision", "DynamicWindow", "GridMap", "validate_control", "ErgodicControl", "Gaussian", "GridBounds", "Omni", "PhikPlan", "SimpleCart", "Target", "fp64_peak",
+    "Collision", "DynamicWindow", "GridMap", "integrate_twist", "validate_control", "ErgodicControl", "Gaussian", "GridBounds", "Omni", "PhikPlan", "SimpleCart", "Target", "fp64_peak",
     "ErgodicB200Error", "MODEL_OMNI", "MODEL_SIMPLE_CART", "EB_OK", "EB_ERR_CUDA",
     "EB_ERR_INVALID_ARGUMENT", "EB_ERR_NO_DEVICE",
 ]

@@ -126,6 +126,7 @@ SIGNATURES = {
     "eb_basis_spatial_coeff_host": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, _vp, _vp, C.c_longlong, _vp]),
     "eb_target_fill_host": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_longlong, _vp]),
     "eb_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
+    "eb_integrate_twist_dev": (C.c_int, [C.c_int, _vp, _vp, C.c_double, C.c_int, _vp, _vp]),
     "eb_dwa_control_twist_host": (C.c_int, [_vp, C.POINTER(EbCollision), C.POINTER(EbDwa), _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "eb_dwa_control_twist_dev": (C.c_int, [_vp, C.POINTER(EbCollision), C.POINTER(EbDwa), _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "eb_dwa_control_traj_host": (C.c_int, [_vp, C.POINTER(EbCollision), C.POINTER(EbDwa), _vp, _vp, _vp, C.c_int, C.c_int,

@@ -210,3 +210,17 @@ class DynamicWindow:
             raise ValueError(self._lib.eb_last_error().decode())
         check(st)
         return found, u
+
+
+def integrate_twist(x, u, dt: float, out=None):
+    """numerics.hpp:273-298 + the angle wrap :77-89 for (B, 3) torch CUDA poses and twists, on the
+    current stream; ``out`` may be ``x`` itself"""
+    assert _is_cuda(x) and _is_cuda(u) and x.dtype == torch.float64 and u.dtype == torch.float64
+    assert x.is_contiguous() and u.is_contiguous() and x.numel() == u.numel()
+    if out is None:
+        out = torch.empty_like(x)
+    dev = x.device.index or 0
+    s = torch.cuda.current_stream(dev).cuda_stream
+    check(capi.load().eb_integrate_twist_dev(dev, C.c_void_p(x.data_ptr()), C.c_void_p(u.data_ptr()), float(dt),
+                                             x.numel() // 3, C.c_void_p(out.data_ptr()), C.c_void_p(s)))
+    return out

@@ -249,6 +249,22 @@ __global__ void __launch_bounds__(128) validate_control_kernel(const CollisionPa
   p.out[i] = ok;
 }
 
+// integrate_twist + normalize_angle_PI for a batch of poses (numerics.hpp:273-298, 77-89): the
+// constant-twist step the reference uses wherever a pose is propagated (validate_control,
+// DynamicWindow, and the closed-loop harness of bench.py --workload c5loop).  In place is fine.
+__global__ void __launch_bounds__(256) integrate_twist_kernel(const double* __restrict__ x, const double* __restrict__ u,
+                                                              double dt, int count, double* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double px = x[(size_t)i * 3 + 0], py = x[(size_t)i * 3 + 1], th = x[(size_t)i * 3 + 2];
+  const TwistStep step(u[(size_t)i * 3 + 0], u[(size_t)i * 3 + 1], u[(size_t)i * 3 + 2], dt);
+  step.advance(px, py, th);
+  out[(size_t)i * 3 + 0] = px;
+  out[(size_t)i * 3 + 1] = py;
+  out[(size_t)i * 3 + 2] = th;
+}
+
 // ---- DynamicWindow::control (dynamic_window.cpp:93-187) ---------------------------------
 // One warp per instance; the lanes stride over the vx * vy * vth candidate twists of the
 // window (:189-235), each lane rolls its candidates out (objective :237-286: constant twist,

@@ -1635,6 +1635,20 @@ eb_status eb_validate_control_host(eb_grid* g, const eb_collision* c, const doub
   return EB_OK;
 }
 
+// integrate_twist + normalize_angle_PI (numerics.hpp:273-298, 77-89), batched, on `stream`
+eb_status eb_integrate_twist_dev(int device, const double* x_dev, const double* u_dev, double dt, int count,
+                                 double* out_dev, void* cuda_stream)
+{
+  if (count < 0 || (count > 0 && (!x_dev || !u_dev || !out_dev)))
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_integrate_twist_dev: bad arguments");
+  if (count == 0) return EB_OK;
+  EB_CUDA(cudaSetDevice(device));
+  eb::integrate_twist_kernel<<<(count + 255) / 256, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(x_dev, u_dev, dt,
+                                                                                                      count, out_dev);
+  EB_CUDA(cudaGetLastError());
+  return EB_OK;
+}
+
 // ---- DynamicWindow::control (dynamic_window.cpp:93-187) -----------------------------
 }  // extern "C"
 

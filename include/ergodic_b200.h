@@ -274,6 +274,11 @@ long long eb_grid_launch_count(const eb_grid *g);
  * 2 = always. */
 eb_status eb_grid_set_dilation(eb_grid *g, int mode);
 
+/* integrate_twist + normalize_angle_PI (numerics.hpp:273-298, 77-89) for 3 x count poses and twists on the
+ * device (out may alias x): the constant-twist step of validate_control / DynamicWindow, exported for closed loops */
+eb_status eb_integrate_twist_dev(int device, const double *x_dev, const double *u_dev, double dt, int count,
+                                 double *out_dev, void *cuda_stream);
+
 /* ---- DynamicWindow -----------------------------------
  * Batched DynamicWindow::control (dynamic_window.cpp:93-187): for every instance the
  * vx x vy x vth candidate twists of its dynamic window (:189-235) are rolled out as

@@ -125,3 +125,29 @@ def test_validate_control_large_map_properties():
         long_ok.cpu().numpy()[sample],
         Oracle.validate_control(data, res, -100.0, -100.0, (0.2, 1.0, 0.05, 0.65), x0.cpu().numpy()[sample],
                                 u.cpu().numpy()[sample], 0.1, 2.0))
+
+
+def test_integrate_twist_matches_cpu():
+    """the constant-twist step + wrap (numerics.hpp:273-298, 77-89), both branches; sin / cos differ from
+    glibc's by an ulp or two, everything else is rounded as the reference rounds it"""
+    import torch
+
+    import ergodic_exploration_b200 as eb
+
+    rng = np.random.default_rng(8)
+    n = 5000
+    x = np.column_stack([rng.uniform(-50, 50, n), rng.uniform(-50, 50, n), rng.uniform(-np.pi, np.pi, n)])
+    u = np.column_stack([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), rng.uniform(-2, 2, n)])
+    u[::4, 2] = 0.0
+    got = eb.integrate_twist(torch.from_numpy(x).cuda(), torch.from_numpy(u).cuda(), 0.1).cpu().numpy()
+    want = np.empty_like(x)
+    for i in range(n):
+        w = Oracle.integrate_twist(x[i], u[i], 0.1)
+        w[2] = Oracle.normalize_angle_pi(w[2])
+        want[i] = w
+    assert np.max(np.abs(got[:, :2] - want[:, :2])) <= 1e-13
+    d = got[:, 2] - want[:, 2]
+    assert np.max(np.abs(np.arctan2(np.sin(d), np.cos(d)))) <= 1e-13
+    xd = torch.from_numpy(x).cuda()
+    eb.integrate_twist(xd, torch.from_numpy(u).cuda(), 0.1, out=xd)  # in place
+    np.testing.assert_array_equal(xd.cpu().numpy(), got)

@@ -15,4 +15,6 @@ for w in c2 c5 c4; do
   ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 4 -c 1 -f -o gpurun_out/solve_$w python bench.py --workload $w --steps 3 --warmup 3 > gpurun_out/ncu_$w.log 2>&1
 done
 ncu --set full --clock-control none --import-source on -k regex:phik_dmma -s 3 -c 1 -f -o gpurun_out/phik_c3 python bench.py --workload c3 --steps 3 --warmup 3 > gpurun_out/ncu_c3.log 2>&1
-ls gpurun_out | head -50
+
+ncu --set full --clock-control none --import-source on -k regex:"dwa_control|inflate_scatter|validate_control" -c 3 -f -o gpurun_out/avoid python bench.py --workload dwa --steps 2 --warmup 3 > gpurun_out/ncu_dwa.log 2>&1
+ls gpurun_out | head -60
