@@ -229,6 +229,9 @@ __device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, const int
 #ifndef EB_DMMA_GRAD
 #define EB_DMMA_GRAD 1
 #endif
+#ifndef EB_DMMA_GRAD_SMALL
+#define EB_DMMA_GRAD_SMALL 0
+#endif
 #ifndef EB_KB_16
 #define EB_KB_16 8
 #endif
@@ -252,7 +255,7 @@ struct SolveCfg
   // gradient on the FP64 tensor cores (see "DMMA gradient" in solve_kernel): pays when the
   // 8-row / 4-order tile padding is small, i.e. not for nb <= 12; nb = 32 would need 128
   // registers of S fragments
-  static constexpr bool kDmmaGrad = EB_DMMA_GRAD && (NB == 16 || NB == 20 || NB == 24);
+  static constexpr bool kDmmaGrad = EB_DMMA_GRAD && (NB == 16 || NB == 20 || NB == 24 || (EB_DMMA_GRAD_SMALL && NB <= 12));
   // per-warp table region: the two c_k tables (pitch 20, 16 slots) or the four gradient
   // tables (pitch 12, 8 slots), whichever is larger; S (NB x NB) aliases it
   static constexpr int kTabDoubles = kDmmaGrad ? 4 * NB * kGradPitch : 2 * NB * kTabStride;
