@@ -416,7 +416,9 @@ def run_ours(args, wl, rank, world, local_rank):
         "e2e": {"value": world * B * args.steps / e2e_s, "unit": "solves/s",
                 "h2d_bytes_per_step": B * 3 * 8, "d2h_bytes_per_step": B * 3 * 8 + 4,
                 "ms_per_step": e2e_s / args.steps * 1e3,
-                "path": "eb_control_host: pinned host x -> H2D -> fused kernel -> D2H u0 + fault flag -> sync"},
+                "path": ("eb_control_host with pinned host buffers: the fused kernel reads x and writes u0 in place over "
+                         "PCIe (zero-copy, batch <= 16384), fault flag in mapped memory, stream sync") if B <= 16384 else
+                        "eb_control_host: pinned host x -> H2D -> fused kernel -> D2H u0 + fault flag -> sync"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"kernel": "solve_kernel", "bound": "fp64", "achieved": achieved, "peak": peak,
