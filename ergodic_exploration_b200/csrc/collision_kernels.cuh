@@ -34,6 +34,13 @@ namespace eb
 {
 constexpr int kPruneVerified = 3000;  // radii for which the r - 1/2 bound has been checked exhaustively
 
+// last radius worth walking: min(r_max, r_col) where the r - 1/2 bound has been verified and the
+// collision radius is a plain non-negative one; otherwise the reference's full range
+__host__ __device__ inline int prune_radius(int r_col, int r_max)
+{
+  return (r_col >= 0 && r_col + 1 < kPruneVerified) ? (r_max < r_col ? r_max : r_col) : r_max;
+}
+
 struct GridView
 {
   const signed char* data;  // [ysize][xsize]
@@ -99,7 +106,7 @@ __device__ __forceinline__ bool collision_check_pose(const CollisionParams& p, d
     return __ldg(p.inflated + (size_t)py * (size_t)pw + (size_t)px) != 0;
   }
   // Collision::search (:150-167), pruned to the radii that can satisfy sqrd_obs <= r_col^2
-  const int r_last = (p.r_col + 1 < kPruneVerified) ? min(p.r_max, p.r_col) : p.r_max;
+  const int r_last = prune_radius(p.r_col, p.r_max);
   for (int r0 = p.r_bnd; r0 <= r_last; r0++)
   {
     // Collision::bresenhamCircle (:169-215)

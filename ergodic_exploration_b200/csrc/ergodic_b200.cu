@@ -1377,7 +1377,7 @@ eb_status collision_params(const eb_grid* g, const eb_collision* c, eb::Collisio
 // build = false it is used only when it already exists for exactly these parameters.
 eb_status use_inflated(eb_grid* g, eb::CollisionParams* p, bool build)
 {
-  const int r_last = (p->r_col + 1 < eb::kPruneVerified) ? std::min(p->r_max, p->r_col) : p->r_max;
+  const int r_last = eb::prune_radius(p->r_col, p->r_max);
   const bool match = g->infl_valid && g->infl_key[0] == p->r_bnd && g->infl_key[1] == r_last &&
                      g->infl_key[2] == p->r_col && g->infl_thr == p->occupied_threshold;
   if (g->dilation_mode == 1) return EB_OK;

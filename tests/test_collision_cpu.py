@@ -49,6 +49,7 @@ CASES = [
     (64, 48, 0.1, 0.0, 0.0, (0.25, 0.25, 0.0, 0.5)),        # search == boundary, one circle
     (200, 200, 0.05, -5.0, -5.0, (0.03, 0.4, 0.3, 0.65)),   # r_bnd = 0, r_col > r_bnd
     (90, 130, 0.2, 3.3, -7.1, (0.5, 2.0, 0.1, 0.0)),        # threshold 0: every non-negative cell counts
+    (70, 70, 0.1, 0.0, 0.0, (0.3, 0.6, -0.55, 0.5)),        # negative collision radius: r_col^2 still compares
 ]
 
 
