@@ -1287,7 +1287,11 @@ eb_status eb_control_dev_gather(eb_controller* c, eb_peer_group* g, double xmin,
     pp.my_flags = g->flags;
     pp.need = need;
     pp.done_counter = g->side_counter;
-    const int blocks = (int)std::max<long long>(1, std::min<long long>(32, (g->elems / 2 + 255) / 256));
+    // Few blocks on purpose: a single-wave solve kernel needs nearly every resident-CTA slot of the
+    // machine (1024 of 1036 at 4096 instances), and a publish block that is still running -- or
+    // waiting in the reuse guard for a slower rank -- when the next solve kernel starts must fit
+    // into the spare slots, or that kernel spills into a second wave.
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(4, (g->elems / 2 + 4095) / 4096));
     eb::peer_publish_kernel<<<blocks, 256, 0, g->side>>>(pp);
     EB_CUDA(cudaGetLastError());
     EB_CUDA(cudaEventRecord(g->published[parity], g->side));
