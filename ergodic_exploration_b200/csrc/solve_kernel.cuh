@@ -22,9 +22,15 @@
 //    warp contracts them with FP64 tensor-core tiles (mma.sync m8n8k4 ->
 //    DMMA.8x8x4), accumulators in registers.
 //  * the metric gradient is a pair of bilinear forms per step,
-//    sx^T (a.S) cy and cx^T (S.b) sy: each lane evaluates them for its own time
-//    step with S broadcast from shared memory, cos/sin rows held in registers.
-// Shared memory per warp: 2*NB*20 + (4 or 8)*32*rounds doubles (SolveCfg).
+//    sx^T (a.S) cy and cx^T (S.b) sy.  nb = 16 / 20 / 24: S sits in registers as
+//    DMMA A fragments and 8-step tiles of cos / sin tables are contracted on the
+//    tensor cores ("DMMA gradient" below); otherwise each lane evaluates them for
+//    its own time step with S broadcast from shared memory, cos/sin rows of a kx
+//    block held in registers.
+//  * N > 1 GPUs: the first twists are published to every rank over NVLink peer
+//    memory by this kernel itself (peer_gather.cuh).
+// Shared memory per warp: SolveCfg::kTabDoubles (the c_k or the gradient tables,
+// S aliases them) + (4 or 8)*32*rounds doubles of per-step records.
 #pragma once
 
 #include "common.cuh"
