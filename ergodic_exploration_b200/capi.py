@@ -21,6 +21,8 @@ EB_ERR_UNSUPPORTED = 5
 
 MODEL_SIMPLE_CART = 0
 MODEL_OMNI = 1
+MODEL_CART = 2
+MODEL_MECANUM = 3
 
 
 class EbConfig(C.Structure):
@@ -142,6 +144,23 @@ SIGNATURES = {
     "eb_peer_group_wait": (C.c_int, [_vp, _vp, C.c_ulonglong]),
     "eb_peer_gathered_dev": (_vp, [_vp, C.c_ulonglong]),
     "eb_peer_group_steps": (C.c_ulonglong, [_vp]),
+    "eb_peer_group_fused": (C.c_int, [_vp, C.c_int]),
+    "eb_phik_plan_create_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                         C.c_double, C.c_int, C.c_double, C.c_double, C.POINTER(_vp)]),
+    "eb_map_target_create": (C.c_int, [C.c_int, C.c_uint, C.c_uint, C.c_double, C.c_int, C.POINTER(_vp)]),
+    "eb_map_target_destroy": (None, [_vp]),
+    "eb_map_target_set_stream": (C.c_int, [_vp, _vp]),
+    "eb_map_target_execute_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "eb_map_target_execute_host": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "eb_map_target_density_dev": (_vp, [_vp]),
+    "eb_map_target_extent": (C.c_int, [_vp, _dp, _dp]),
+    "eb_map_target_launch_count": (C.c_longlong, [_vp]),
+    "eb_set_phik_dev": (C.c_int, [_vp, _vp, C.c_double, C.c_double]),
+    "eb_model_controls": (C.c_int, [C.c_int]),
+    "eb_rk4_solve_host": (C.c_int, [C.c_int, C.c_int, _vp, C.c_double, C.c_double, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "eb_rk4_solve_dev": (C.c_int, [C.c_int, C.c_int, _vp, C.c_double, C.c_double, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "eb_model_eval_host": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "eb_l2_gather_peak": (C.c_int, [C.c_int, _dp]),
     "eb_grid_create": (C.c_int, [C.c_int, _vp, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.POINTER(_vp)]),
     "eb_grid_update": (C.c_int, [_vp, _vp]),
     "eb_grid_destroy": (None, [_vp]),

@@ -20,7 +20,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import capi
-from .capi import MODEL_OMNI, MODEL_SIMPLE_CART, EbConfig, ErgodicB200Error, check
+from .capi import MODEL_CART, MODEL_MECANUM, MODEL_OMNI, MODEL_SIMPLE_CART, EbConfig, ErgodicB200Error, check
 
 try:  # torch is plumbing only (device memory, streams); optional for the host path
     import torch
@@ -49,18 +49,119 @@ class Target:
         del self.gaussians[idx]
 
 
-class SimpleCart:
+class _Model:
+    """operator() / fdx / fdu / wheels2Twist of the reference's model structs, evaluated by model_eval_kernel
+    (csrc/model_kernels.cuh) for one state or a batch (rows)."""
+
+    model_id = -1
+    state_space = 3
+    params = ()
+
+    def _eval(self, x, u, want):
+        lib = capi.load()
+        nu = lib.eb_model_controls(self.model_id)
+        x = _np_f64(x).reshape(-1, 3)
+        u = _np_f64(u).reshape(-1, nu)
+        n = x.shape[0]
+        if u.shape[0] != n:
+            raise ValueError("x and u need the same number of rows")
+        f, A, B, vb = np.empty((n, 3)), np.empty((n, 3, 3)), np.empty((n, nu, 3)), np.empty((n, 3))
+        par = _np_f64(self.params) if len(self.params) else None
+        st = lib.eb_model_eval_host(0, self.model_id, par.ctypes.data if par is not None else None, x.ctypes.data,
+                                    u.ctypes.data, n, f.ctypes.data if "f" in want else None,
+                                    A.ctypes.data if "A" in want else None, B.ctypes.data if "B" in want else None,
+                                    vb.ctypes.data if "vb" in want else None)
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(lib.eb_last_error().decode())  # std::invalid_argument (cart.hpp:167-170)
+        check(st)
+        # column-major 3 x 3 / 3 x nu blocks -> numpy (row, col)
+        return f, np.transpose(A, (0, 2, 1)), np.transpose(B, (0, 2, 1)), vb
+
+    def __call__(self, x, u):
+        f = self._eval(x, u, "f")[0]
+        return f[0] if np.ndim(x) == 1 else f
+
+    def fdx(self, x, u):
+        A = self._eval(x, u, "A")[1]
+        return A[0] if np.ndim(x) == 1 else A
+
+    def fdu(self, x):
+        nu = capi.load().eb_model_controls(self.model_id)
+        xs = _np_f64(x).reshape(-1, 3)
+        B = self._eval(xs, np.zeros((xs.shape[0], nu)), "B")[2]
+        return B[0] if np.ndim(x) == 1 else B
+
+    def wheels2Twist(self, u):
+        nu = capi.load().eb_model_controls(self.model_id)
+        us = _np_f64(u).reshape(-1, nu)
+        vb = self._eval(np.zeros((us.shape[0], 3)), us, "vb")[3]
+        return vb[0] if np.ndim(u) == 1 else vb
+
+
+class SimpleCart(_Model):
     """models/cart.hpp:152-206"""
 
     model_id = MODEL_SIMPLE_CART
-    state_space = 3
 
 
-class Omni:
+class Omni(_Model):
     """models/omni.hpp:164-215"""
 
     model_id = MODEL_OMNI
-    state_space = 3
+
+
+class Cart(_Model):
+    """models/cart.hpp:60-145 -- 2-wheel differential drive, controls = wheel velocities [uL, uR]"""
+
+    model_id = MODEL_CART
+
+    def __init__(self, wheel_radius: float, wheel_base: float):
+        self.wheel_radius, self.wheel_base = float(wheel_radius), float(wheel_base)
+        self.params = (self.wheel_radius, self.wheel_base)
+
+
+class Mecanum(_Model):
+    """models/omni.hpp:59-157 -- 4 mecanum wheels, controls = wheel velocities [u0..u3]"""
+
+    model_id = MODEL_MECANUM
+
+    def __init__(self, wheel_radius: float, wheel_base_x: float, wheel_base_y: float):
+        self.wheel_radius, self.wheel_base_x, self.wheel_base_y = float(wheel_radius), float(wheel_base_x), float(wheel_base_y)
+        self.params = (self.wheel_radius, self.wheel_base_x, self.wheel_base_y)
+
+
+class RungeKutta:
+    """integrator.hpp:60-129 -- the forward problem: solve(model, x0, ut, horizon) -> xt (steps, 3), batched when
+    x0 has rows.  Every step is computed by rk4_solve_kernel (one thread per instance)."""
+
+    def __init__(self, dt: float):
+        self.dt = float(dt)
+
+    def solve(self, model, x0, ut, horizon: float, device: int = 0):
+        lib = capi.load()
+        nu = lib.eb_model_controls(model.model_id)
+        steps = int(abs(horizon / self.dt))
+        single = np.ndim(x0) == 1
+        x0 = _np_f64(x0).reshape(-1, 3)
+        n = x0.shape[0]
+        ut = _np_f64(ut)
+        per_instance = ut.ndim == 3
+        if ut.shape[-2:] != (steps, nu) and ut.shape[-2:] == (nu, steps):
+            ut = np.ascontiguousarray(np.swapaxes(ut, -1, -2))  # Armadillo nu x steps -> (steps, nu) rows
+        if ut.shape[-2:] != (steps, nu) or (per_instance and ut.shape[0] != n):
+            raise ValueError(f"ut must be (steps={steps}, nu={nu}) or (count, steps, nu)")
+        xt = np.empty((n, steps, 3))
+        par = _np_f64(model.params) if len(model.params) else None
+        st = lib.eb_rk4_solve_host(device, model.model_id, par.ctypes.data if par is not None else None, self.dt,
+                                   float(horizon), x0.ctypes.data, ut.ctypes.data, int(per_instance), n, xt.ctypes.data)
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(lib.eb_last_error().decode())
+        check(st)
+        return xt[0] if single else xt
+
+    def step(self, model, x, u):
+        """one RK4 step (integrator.hpp:176-184), heading NOT wrapped (solve wraps)"""
+        raise NotImplementedError("use solve(); the unwrapped single step is not exported")
 
 
 @dataclass
@@ -263,6 +364,11 @@ class ErgodicControl:
         return ph, lx.value, ly.value
 
     def set_phik(self, phik, lx: float, ly: float) -> None:
+        if _is_cuda_tensor(phik):  # e.g. the output of MapTarget.execute / PhikPlan.execute: no host round trip
+            self._sync_stream()
+            assert phik.dtype == torch.float64 and phik.is_contiguous() and phik.numel() == self.num_coeff
+            check(self._lib.eb_set_phik_dev(self._h, C.c_void_p(phik.data_ptr()), float(lx), float(ly)))
+            return
         ph = _np_f64(phik).reshape(self.num_coeff)
         check(self._lib.eb_set_phik(self._h, ph.ctypes.data, float(lx), float(ly)))
 
@@ -345,6 +451,66 @@ class PhikPlan:
         f, d = C.c_int(0), C.c_double(0.0)
         check(self._lib.eb_phik_plan_fold(self._h, C.byref(f), C.byref(d)))
         return bool(f.value), d.value
+
+
+class MapTarget:
+    """Map-derived target: int8 occupancy grid -> entropy per cell (numerics.hpp:164-179
+    over GridMap::getCell) -> normalised density -> phi_k, all on the device.  One execute per map update."""
+
+    def __init__(self, xsize: int, ysize: int, resolution: float, nb: int, device: int = 0):
+        self._lib = capi.load()
+        h = C.c_void_p()
+        st = self._lib.eb_map_target_create(device, int(xsize), int(ysize), float(resolution), int(nb), C.byref(h))
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(self._lib.eb_last_error().decode())
+        check(st)
+        self._h, self.xsize, self.ysize, self.nb, self.device = h, int(xsize), int(ysize), int(nb), int(device)
+        self.lx, self.ly = xsize * float(resolution), ysize * float(resolution)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.eb_map_target_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def execute(self, cells, phik=None):
+        """cells: (ysize, xsize) int8, torch CUDA tensor (device path, current stream) or numpy (host path)"""
+        if _is_cuda_tensor(cells):
+            s = torch.cuda.current_stream(self.device).cuda_stream
+            check(self._lib.eb_map_target_set_stream(self._h, C.c_void_p(s)))
+            assert cells.dtype == torch.int8 and cells.is_contiguous() and cells.numel() == self.xsize * self.ysize
+            if phik is None:
+                phik = torch.empty(self.nb * self.nb, dtype=torch.float64, device=cells.device)
+            check(self._lib.eb_map_target_execute_dev(self._h, C.c_void_p(cells.data_ptr()), C.c_void_p(phik.data_ptr()), None))
+            return phik
+        cells = np.ascontiguousarray(cells, dtype=np.int8).reshape(self.ysize, self.xsize)
+        out = np.empty(self.nb * self.nb)
+        s = C.c_double(0.0)
+        check(self._lib.eb_map_target_execute_host(self._h, cells.ctypes.data, out.ctypes.data, C.byref(s)))
+        self.last_sum = s.value
+        return out
+
+    def density(self):
+        """the un-normalised entropy density of the last execute, (ysize, xsize) torch view of device memory"""
+        from .sharding import _DevView
+        ptr = self._lib.eb_map_target_density_dev(self._h)
+        return torch.as_tensor(_DevView(ptr, (self.ysize, self.xsize)), device=torch.device("cuda", self.device))
+
+    def launch_count(self) -> int:
+        return int(self._lib.eb_map_target_launch_count(self._h))
+
+
+def l2_gather_peak(device: int = 0) -> float:
+    """measured G sectors/s of random 1-byte loads over a 16 MB L2-resident buffer"""
+    lib = capi.load()
+    v = C.c_double(0)
+    check(lib.eb_l2_gather_peak(device, C.byref(v)))
+    return v.value
 
 
 def fp64_peak(device: int = 0):

@@ -23,6 +23,9 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // inclusive prefix sum over the lanes of a warp (lane 0 first)
 __device__ __forceinline__ double warp_scan_incl(double v, int lane)
 {
+#if defined(EB_ABL) && (EB_ABL & 64)
+  return v + (double)lane;  // ablation timing only
+#endif
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1)
   {
@@ -35,6 +38,9 @@ __device__ __forceinline__ double warp_scan_incl(double v, int lane)
 // inclusive suffix sum over the lanes of a warp (lane 31 first)
 __device__ __forceinline__ double warp_scan_incl_rev(double v, int lane)
 {
+#if defined(EB_ABL) && (EB_ABL & 64)
+  return v - (double)lane;  // ablation timing only
+#endif
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1)
   {
@@ -74,6 +80,11 @@ __constant__ double kTrigR[5] = { 6.36619772367581382433e-01,   // 2/pi
 
 __device__ __forceinline__ void sincos_kernel(double r, int n, double* s, double* c)
 {
+#if defined(EB_ABL) && (EB_ABL & 8)
+  *s = r * (double)(n + 1);  // ablation timing only: no polynomial (wrong values)
+  *c = 1.0 - r;
+  return;
+#endif
   const double z = r * r;
   double ps = fma(z, kTrigS[5], kTrigS[4]);
   double pc = fma(z, kTrigC[5], kTrigC[4]);

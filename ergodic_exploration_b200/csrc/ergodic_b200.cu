@@ -19,11 +19,16 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges show up under Nsight, cost ~nothing otherwise
+
 #include "collision_kernels.cuh"
+#include "map_target.cuh"
+#include "model_kernels.cuh"
 #include "peer_gather.cuh"
 #include "phik_dmma.cuh"
 #include "phik_kernels.cuh"
 #include "solve_kernel.cuh"
+#include "solve_kernel_v2.cuh"
 
 namespace
 {
@@ -49,6 +54,14 @@ eb_status fail(eb_status st, const std::string& msg)
     }                                                                                                   \
   } while (0)
 
+// NVTX range around a C-ABI call (tracing hook)
+struct NvtxRange
+{
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define EB_TRACE(name) NvtxRange nvtx_range__(name)
+
 // grid.hpp:61-64
 unsigned axis_length(double lower, double upper, double resolution)
 {
@@ -59,10 +72,10 @@ unsigned axis_length(double lower, double upper, double resolution)
 bool almost_equal(double a, double b) { return std::fabs(a - b) < 1.0e-12; }
 
 // configTarget's accumulated grid coordinates (ergodic_control.hpp:394-407)
-std::vector<double> accumulated_axis(int n, double resolution)
+std::vector<double> accumulated_axis(int n, double resolution, double start = 0.0)
 {
   std::vector<double> v(n);
-  double x = 0.0;
+  double x = start;
   for (int i = 0; i < n; i++)
   {
     v[i] = x;
@@ -152,6 +165,13 @@ eb_status eb_phik_plan_create(int device, int nx, int ny, double resolution, dou
 eb_status eb_phik_plan_create_rows(int device, int nx, int ny_total, int row_begin, int ny, double resolution,
                                    double lx, double ly, int nb, eb_phik_plan** out)
 {
+  return eb_phik_plan_create_ex(device, nx, ny_total, row_begin, ny, resolution, lx, ly, nb, 0.0, 0.0, out);
+}
+
+eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin, int ny, double resolution, double lx,
+                                 double ly, int nb, double x_first, double y_first, eb_phik_plan** out)
+{
+  EB_TRACE("eb_phik_plan_create");
   if (!out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create: out is NULL");
   *out = nullptr;
   if (nx < 1 || ny < 1 || nb < 1 || nb > 32)
@@ -175,8 +195,8 @@ eb_status eb_phik_plan_create_rows(int device, int nx, int ny_total, int row_beg
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   p->max_parts = std::max(1, sms);
-  const std::vector<double> xs = accumulated_axis(nx, resolution);
-  const std::vector<double> ys_all = accumulated_axis(row_begin + ny, resolution);
+  const std::vector<double> xs = accumulated_axis(nx, resolution, x_first);
+  const std::vector<double> ys_all = accumulated_axis(row_begin + ny, resolution, y_first);
   const std::vector<double> ys(ys_all.begin() + row_begin, ys_all.end());
   auto cleanup = [&](eb_status st) {
     eb_phik_plan_destroy(p);
@@ -303,6 +323,7 @@ eb_status eb_phik_execute_raw_dev(eb_phik_plan* p, const double* phi_dev, double
 static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* phik_dev, double* phi_sum_dev,
                               double* raw_dev)
 {
+  EB_TRACE("eb_phik_execute");
   EB_CUDA(cudaSetDevice(p->device));
   int algo = p->algo;
   if (algo == 0) algo = (eb::phik_dmma_supported(p->nx, p->ny) && (long long)p->nx * p->ny >= (1 << 18)) ? 2 : 1;
@@ -329,6 +350,7 @@ static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* ph
 
 eb_status eb_phik_execute_host(eb_phik_plan* p, const double* phi, double* phik, double* phi_sum)
 {
+  EB_TRACE("eb_phik_execute_host");
   if (!p || !phi || !phik) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_execute_host: NULL argument");
   EB_CUDA(cudaSetDevice(p->device));
   double* d_phi = nullptr;
@@ -431,37 +453,86 @@ inline int zero_copy_max_batch()
 
 namespace
 {
-template <int MODEL, int NB>
-cudaError_t launch_solve_t(const eb::SolveParams& p, int rounds, cudaStream_t s)
+// num_basis 13..24 run solve_kernel2 (solve_kernel_v2.cuh); EB_SOLVE_V1=1 keeps the round-1 kernel for A/B timing
+inline bool use_v2(int nb)
 {
-  const size_t smem = eb::solve_smem_bytes(eb::SolveCfg<NB>::kTabDoubles, eb::SolveCfg<NB>::kFields, rounds);
-  // the attribute is per device: remember what has been set, per instantiation and device
-  static size_t configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (smem > configured[dev & 63])
-  {
-    cudaError_t e =
-        cudaFuncSetAttribute(eb::solve_kernel<MODEL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured[dev & 63] = smem;
-  }
-  const int grid = (p.B + eb::kSolveWarps - 1) / eb::kSolveWarps;
-  eb::solve_kernel<MODEL, NB><<<grid, eb::kSolveWarps * 32, smem, s>>>(p);
-  return cudaGetLastError();
+  static const bool v1 = [] {
+    const char* e = std::getenv("EB_SOLVE_V1");
+    return e && std::atoi(e) != 0;
+  }();
+  return !v1 && nb > 12 && nb <= 24;
 }
+
+template <int MODEL, int NB, bool V2>
+struct SolveLaunch
+{
+  static size_t smem(int rounds)
+  {
+    if constexpr (V2)
+      return eb::solve_smem_bytes(eb::Solve2Cfg<NB>::kTabDoubles, eb::Solve2Cfg<NB>::kFields, rounds);
+    else
+      return eb::solve_smem_bytes(eb::SolveCfg<NB>::kTabDoubles, eb::SolveCfg<NB>::kFields, rounds);
+  }
+  static cudaError_t launch(const eb::SolveParams& p, int rounds, cudaStream_t s)
+  {
+    const size_t bytes = smem(rounds);
+    // the attribute is per device: remember what has been set, per instantiation and device
+    static size_t configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto kernel = [] {
+      if constexpr (V2)
+        return eb::solve_kernel2<MODEL, NB>;
+      else
+        return eb::solve_kernel<MODEL, NB>;
+    }();
+    if (bytes > configured[dev & 63])
+    {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e != cudaSuccess) return e;
+      configured[dev & 63] = bytes;
+    }
+    const int grid = (p.B + eb::kSolveWarps - 1) / eb::kSolveWarps;
+    kernel<<<grid, eb::kSolveWarps * 32, bytes, s>>>(p);
+    return cudaGetLastError();
+  }
+};
 
 template <int MODEL>
 cudaError_t launch_solve_m(const eb::SolveParams& p, int rounds, cudaStream_t s)
 {
   const int nb = p.nb;
-  if (nb <= 8) return launch_solve_t<MODEL, 8>(p, rounds, s);
-  if (nb <= 10) return launch_solve_t<MODEL, 10>(p, rounds, s);
-  if (nb <= 12) return launch_solve_t<MODEL, 12>(p, rounds, s);
-  if (nb <= 16) return launch_solve_t<MODEL, 16>(p, rounds, s);
-  if (nb <= 20) return launch_solve_t<MODEL, 20>(p, rounds, s);
-  if (nb <= 24) return launch_solve_t<MODEL, 24>(p, rounds, s);
-  return launch_solve_t<MODEL, 32>(p, rounds, s);
+  if (nb <= 8) return SolveLaunch<MODEL, 8, false>::launch(p, rounds, s);
+  if (nb <= 10) return SolveLaunch<MODEL, 10, false>::launch(p, rounds, s);
+  if (nb <= 12) return SolveLaunch<MODEL, 12, false>::launch(p, rounds, s);
+  if (use_v2(nb))
+  {
+    if (nb <= 16) return SolveLaunch<MODEL, 16, true>::launch(p, rounds, s);
+    if (nb <= 20) return SolveLaunch<MODEL, 20, true>::launch(p, rounds, s);
+    return SolveLaunch<MODEL, 24, true>::launch(p, rounds, s);
+  }
+  if (nb <= 16) return SolveLaunch<MODEL, 16, false>::launch(p, rounds, s);
+  if (nb <= 20) return SolveLaunch<MODEL, 20, false>::launch(p, rounds, s);
+  if (nb <= 24) return SolveLaunch<MODEL, 24, false>::launch(p, rounds, s);
+  return SolveLaunch<MODEL, 32, false>::launch(p, rounds, s);
+}
+
+// dynamic shared memory of the solve kernel instantiation that serves `nb` (same dispatch as launch_solve_m)
+size_t solve_smem_for(int nb, int rounds)
+{
+  if (nb <= 8) return SolveLaunch<0, 8, false>::smem(rounds);
+  if (nb <= 10) return SolveLaunch<0, 10, false>::smem(rounds);
+  if (nb <= 12) return SolveLaunch<0, 12, false>::smem(rounds);
+  if (use_v2(nb))
+  {
+    if (nb <= 16) return SolveLaunch<0, 16, true>::smem(rounds);
+    if (nb <= 20) return SolveLaunch<0, 20, true>::smem(rounds);
+    return SolveLaunch<0, 24, true>::smem(rounds);
+  }
+  if (nb <= 16) return SolveLaunch<0, 16, false>::smem(rounds);
+  if (nb <= 20) return SolveLaunch<0, 20, false>::smem(rounds);
+  if (nb <= 24) return SolveLaunch<0, 24, false>::smem(rounds);
+  return SolveLaunch<0, 32, false>::smem(rounds);
 }
 
 cudaError_t launch_solve(const eb::SolveParams& p, int model, int rounds, cudaStream_t s)
@@ -490,9 +561,13 @@ eb_status ensure_hist(eb_controller* c, long long need)
 eb_status check_fault(eb_controller* c)
 {
   EB_CUDA(cudaStreamSynchronize(c->stream));
-  if (*static_cast<volatile int*>(c->h_fault))
+  const int f = *static_cast<volatile int*>(c->h_fault);
+  if (f)
   {
     *c->h_fault = 0;
+    if (f & 2)  // buffer.cpp:84,103: memory_.at(i) throws std::out_of_range
+      return fail(EB_ERR_OUT_OF_RANGE, "replay-buffer sample index outside [0, stored states)");
+    if (f & 4) return fail(EB_ERR_CUDA, "control(): non-finite state or control signal (NaN / Inf guard)");
     return fail(EB_ERR_INVALID_ARGUMENT, "Invalid twist y-velocity must be 0.");  // cart.hpp:169
   }
   return EB_OK;
@@ -522,6 +597,16 @@ eb_status eb_create(const eb_config* cfg, eb_controller** out)
   if (steps > 4096) return fail(EB_ERR_UNSUPPORTED, "eb_create: more than 4096 horizon steps is not supported");
   if (eb_device_count() < 1) return fail(EB_ERR_NO_DEVICE, "no CUDA device is visible; there is no CPU fallback");
   EB_CUDA(cudaSetDevice(cfg->device));
+  {
+    // the fused kernel keeps per-step records of the whole horizon in shared memory: refuse horizons that cannot fit
+    int optin = 0;
+    EB_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    const size_t need = solve_smem_for(static_cast<int>(cfg->num_basis), (static_cast<int>(steps) + 31) / 32);
+    if (need > static_cast<size_t>(optin))
+      return fail(EB_ERR_UNSUPPORTED, "eb_create: a horizon of " + std::to_string(steps) + " steps with num_basis " +
+                                          std::to_string(cfg->num_basis) + " needs " + std::to_string(need) +
+                                          " bytes of shared memory per block; the device allows " + std::to_string(optin));
+  }
 
   eb_controller* c = new (std::nothrow) eb_controller();
   if (!c) return fail(EB_ERR_CUDA, "out of host memory");
@@ -678,6 +763,7 @@ eb_status eb_set_target_gaussians(eb_controller* c, int n, const double* mu, con
 
 eb_status eb_config_target(eb_controller* c, double xmin, double xmax, double ymin, double ymax, int* rebuilt)
 {
+  EB_TRACE("eb_config_target");
   if (!c) return fail(EB_ERR_INVALID_ARGUMENT, "controller is NULL");
   if (rebuilt) *rebuilt = 0;
   // translation from map to fourier domain (:366-367)
@@ -784,16 +870,19 @@ static eb_status add_state_memory(eb_controller* c, const double* x, cudaMemcpyK
 
 eb_status eb_add_state_memory_host(eb_controller* c, const double* x)
 {
+  EB_TRACE("eb_add_state_memory_host");
   return add_state_memory(c, x, cudaMemcpyHostToDevice);
 }
 eb_status eb_add_state_memory_dev(eb_controller* c, const double* x_dev)
 {
+  EB_TRACE("eb_add_state_memory_dev");
   return add_state_memory(c, x_dev, cudaMemcpyDeviceToDevice);
 }
 
 eb_status eb_control_dev(eb_controller* c, double xmin, double xmax, double ymin, double ymax, const double* x_dev,
                          const int* mem_idx_dev, double* u0_dev, double* metric_dev)
 {
+  EB_TRACE("eb_control_dev");
   if (!c || !x_dev || !u0_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev: NULL argument");
   EB_CUDA(cudaSetDevice(c->cfg.device));
   eb_status st = eb_config_target(c, xmin, xmax, ymin, ymax, nullptr);  // :230
@@ -897,6 +986,7 @@ eb_status eb_check_status(eb_controller* c)
 eb_status eb_control_host(eb_controller* c, double xmin, double xmax, double ymin, double ymax, const double* x,
                           const int* mem_idx, double* u0, double* metric)
 {
+  EB_TRACE("eb_control_host");
   if (!c || !x || !u0) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_host: NULL argument");
   EB_CUDA(cudaSetDevice(c->cfg.device));
   const bool need_idx = mem_idx && c->mem_count > (long long)c->cfg.batch_size;
@@ -929,6 +1019,7 @@ eb_status eb_control_host(eb_controller* c, double xmin, double xmax, double ymi
 
 eb_status eb_opt_traj_dev(eb_controller* c, double* xt_dev)
 {
+  EB_TRACE("eb_opt_traj_dev");
   if (!c || !xt_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_opt_traj_dev: NULL argument");
   EB_CUDA(cudaSetDevice(c->cfg.device));
   const int threads = 128, wpb = threads / 32;
@@ -1252,10 +1343,14 @@ double* eb_peer_gathered_dev(eb_peer_group* g, unsigned long long step)
 
 unsigned long long eb_peer_group_steps(const eb_peer_group* g) { return g ? g->step : 0; }
 
+// 1: a batch of this size publishes from inside the solve kernel, 0: from the group's side stream
+int eb_peer_group_fused(const eb_peer_group* g, int batch) { return (g && batch >= g->fuse_min_batch) ? 1 : 0; }
+
 // control() whose first twists land in every rank's gathered buffer (no collective call)
 eb_status eb_control_dev_gather(eb_controller* c, eb_peer_group* g, double xmin, double xmax, double ymin, double ymax,
                                 const double* x_dev, const int* mem_idx_dev, double* metric_dev)
 {
+  EB_TRACE("eb_control_dev_gather");
   if (!c || !g) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather: NULL argument");
   if (!g->connected) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather: peer group is not connected");
   if (g->elems != 3LL * c->B) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather: peer group sized for another batch");
@@ -1562,6 +1657,7 @@ eb_status eb_grid_set_dilation(eb_grid* g, int mode)
 
 eb_status eb_collision_check_dev(eb_grid* g, const eb_collision* c, const double* poses_dev, int count, int* hit_dev)
 {
+  EB_TRACE("eb_collision_check_dev");
   eb::CollisionParams p{};
   eb_status st = collision_params(g, c, &p);
   if (st != EB_OK) return st;
@@ -1584,6 +1680,7 @@ eb_status eb_collision_check_dev(eb_grid* g, const eb_collision* c, const double
 eb_status eb_validate_control_dev(eb_grid* g, const eb_collision* c, const double* x0_dev, const double* u_dev,
                                   int count, double dt, double horizon, int* valid_dev)
 {
+  EB_TRACE("eb_validate_control_dev");
   eb::CollisionParams p{};
   eb_status st = collision_params(g, c, &p);
   if (st != EB_OK) return st;
@@ -1705,6 +1802,7 @@ eb_status eb_dwa_control_twist_dev(eb_grid* g, const eb_collision* c, const eb_d
                                    const double* vb_dev, const double* vref_dev, int count, int* found_dev,
                                    double* u_opt_dev, double* min_cost_dev)
 {
+  EB_TRACE("eb_dwa_control_twist_dev");
   eb::DwaParams p{};
   eb_status st = dwa_params(g, c, d, count, &p);
   if (st != EB_OK) return st;
@@ -1723,6 +1821,7 @@ eb_status eb_dwa_control_traj_dev(eb_grid* g, const eb_collision* c, const eb_dw
                                   const double* vb_dev, const double* xt_ref_dev, int ncols, int per_instance,
                                   double dt_ref, int count, int* found_dev, double* u_opt_dev, double* min_cost_dev)
 {
+  EB_TRACE("eb_dwa_control_traj_dev");
   eb::DwaParams p{};
   eb_status st = dwa_params(g, c, d, count, &p);
   if (st != EB_OK) return st;
@@ -1734,6 +1833,16 @@ eb_status eb_dwa_control_traj_dev(eb_grid* g, const eb_collision* c, const eb_dw
   p.ncols = ncols;
   p.xt_stride = per_instance ? 3LL * ncols : 0LL;
   p.tf = static_cast<double>(ncols) * dt_ref;  // dynamic_window.cpp:148
+  {
+    // dynamic_window.cpp:276 indexes xt_ref with round((ncols - 1) * t / tf), t accumulated per rollout step; Armadillo's
+    // bounds check throws when the rollout outlasts the reference trajectory -- refuse it here instead of reading past it
+    double t = 0.0;
+    for (int k = 0; k + 1 < p.col.steps; k++) t += p.col.dt;
+    const double jmax = std::round((static_cast<double>(ncols - 1) * t) / p.tf);
+    if (!(jmax <= static_cast<double>(ncols - 1)))
+      return fail(EB_ERR_OUT_OF_RANGE, "eb_dwa_control_traj: the rollout horizon outlasts the reference trajectory "
+                                       "(index past the last column; the reference's Armadillo access throws here)");
+  }
   p.found = found_dev;
   p.u_opt = u_opt_dev;
   p.min_cost = min_cost_dev;
@@ -1792,6 +1901,299 @@ eb_status eb_dwa_control_traj_host(eb_grid* g, const eb_collision* c, const eb_d
   const size_t ref_doubles = 3 * (size_t)ncols * (per_instance ? (size_t)std::max(count, 0) : 1);
   return dwa_host(g, c, d, x0, vb, xt_ref, ref_doubles, true, ncols, per_instance, dt_ref, count, found, u_opt,
                   min_cost);
+}
+
+// ---------------------------------------------------------------------------
+// map-derived target (map_target.cuh), SURVEY.md section 8f-4
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+struct eb_map_target
+{
+  int device = 0, nb = 0;
+  unsigned xsize = 0, ysize = 0;
+  double resolution = 0.0;
+  cudaStream_t stream = nullptr;
+  eb_phik_plan* plan = nullptr;
+  double* d_lut = nullptr;       // entropy of the 256 int8 patterns
+  double* d_phi = nullptr;       // un-normalised density [ysize][xsize]
+  signed char* d_cells = nullptr;  // staging for the _host call
+  double *d_phik = nullptr, *d_sum = nullptr;
+  long long launches = 0;
+};
+
+extern "C" {
+
+eb_status eb_map_target_create(int device, unsigned int xsize, unsigned int ysize, double resolution, int nb,
+                               eb_map_target** out)
+{
+  if (!out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_map_target_create: out is NULL");
+  *out = nullptr;
+  if (xsize < 1 || ysize < 1 || !(resolution > 0.0) || nb < 1 || nb > 32)
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_map_target_create: need xsize, ysize >= 1, resolution > 0, 1 <= nb <= 32");
+  if ((unsigned long long)xsize * ysize > 0x7fffffffull)
+    return fail(EB_ERR_UNSUPPORTED, "eb_map_target_create: more than 2^31 - 1 cells");
+  EB_CUDA(cudaSetDevice(device));
+  eb_map_target* m = new (std::nothrow) eb_map_target();
+  if (!m) return fail(EB_ERR_CUDA, "out of host memory");
+  m->device = device;
+  m->nb = nb;
+  m->xsize = xsize;
+  m->ysize = ysize;
+  m->resolution = resolution;
+  // sample points = cell centres, extent = the map's (grid.cpp:46-61: xmax = xmin + xsize * resolution)
+  eb_status st = eb_phik_plan_create_ex(device, (int)xsize, (int)ysize, 0, (int)ysize, resolution, xsize * resolution,
+                                        ysize * resolution, nb, 0.5 * resolution, 0.5 * resolution, &m->plan);
+  if (st != EB_OK)
+  {
+    delete m;
+    return st;
+  }
+  const size_t cells = (size_t)xsize * ysize;
+  cudaError_t e = cudaMalloc(&m->d_lut, sizeof(double) * 256);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_phi, sizeof(double) * cells);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_phik, sizeof(double) * 1024);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_sum, sizeof(double));
+  if (e == cudaSuccess)
+  {
+    eb::entropy_lut_kernel<<<1, 256>>>(m->d_lut);
+    m->launches += 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess)
+  {
+    eb_map_target_destroy(m);
+    return fail(EB_ERR_CUDA, std::string("eb_map_target_create: ") + cudaGetErrorString(e));
+  }
+  *out = m;
+  return EB_OK;
+}
+
+void eb_map_target_destroy(eb_map_target* m)
+{
+  if (!m) return;
+  cudaSetDevice(m->device);
+  eb_phik_plan_destroy(m->plan);
+  cudaFree(m->d_lut);
+  cudaFree(m->d_phi);
+  cudaFree(m->d_cells);
+  cudaFree(m->d_phik);
+  cudaFree(m->d_sum);
+  delete m;
+}
+
+eb_status eb_map_target_set_stream(eb_map_target* m, void* s)
+{
+  if (!m) return fail(EB_ERR_INVALID_ARGUMENT, "map target is NULL");
+  m->stream = static_cast<cudaStream_t>(s);
+  m->plan->stream = m->stream;
+  return EB_OK;
+}
+
+long long eb_map_target_launch_count(const eb_map_target* m) { return m ? m->launches + m->plan->launches : 0; }
+double* eb_map_target_density_dev(eb_map_target* m) { return m ? m->d_phi : nullptr; }
+
+eb_status eb_map_target_extent(const eb_map_target* m, double* lx, double* ly)
+{
+  if (!m) return fail(EB_ERR_INVALID_ARGUMENT, "map target is NULL");
+  if (lx) *lx = m->xsize * m->resolution;
+  if (ly) *ly = m->ysize * m->resolution;
+  return EB_OK;
+}
+
+eb_status eb_map_target_execute_dev(eb_map_target* m, const signed char* cells_dev, double* phik_dev, double* phi_sum_dev)
+{
+  EB_TRACE("eb_map_target_execute_dev");
+  if (!m || !cells_dev || !phik_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_map_target_execute_dev: NULL argument");
+  EB_CUDA(cudaSetDevice(m->device));
+  const long long cells = (long long)m->xsize * m->ysize;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  const int grid = (int)std::min<long long>((cells / 16 + 255) / 256 + 1, (long long)sms * 8);
+  eb::entropy_density_kernel<<<grid, 256, 0, m->stream>>>(cells_dev, cells, m->d_lut, m->d_phi);
+  m->launches += 1;
+  EB_CUDA(cudaGetLastError());
+  return eb_phik_execute_dev(m->plan, m->d_phi, phik_dev, phi_sum_dev);
+}
+
+eb_status eb_map_target_execute_host(eb_map_target* m, const signed char* cells, double* phik, double* phi_sum)
+{
+  EB_TRACE("eb_map_target_execute_host");
+  if (!m || !cells || !phik) return fail(EB_ERR_INVALID_ARGUMENT, "eb_map_target_execute_host: NULL argument");
+  EB_CUDA(cudaSetDevice(m->device));
+  const size_t n = (size_t)m->xsize * m->ysize;
+  if (!m->d_cells) EB_CUDA(cudaMalloc(&m->d_cells, n));
+  EB_CUDA(cudaMemcpyAsync(m->d_cells, cells, n, cudaMemcpyHostToDevice, m->stream));
+  eb_status st = eb_map_target_execute_dev(m, m->d_cells, m->d_phik, m->d_sum);
+  if (st != EB_OK) return st;
+  EB_CUDA(cudaMemcpyAsync(phik, m->d_phik, sizeof(double) * m->nb * m->nb, cudaMemcpyDeviceToHost, m->stream));
+  if (phi_sum) EB_CUDA(cudaMemcpyAsync(phi_sum, m->d_sum, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  EB_CUDA(cudaStreamSynchronize(m->stream));
+  return EB_OK;
+}
+
+// phi_k from a device buffer (e.g. the output of eb_map_target_execute_dev / eb_phik_execute_dev), no host round trip
+eb_status eb_set_phik_dev(eb_controller* c, const double* phik_dev, double lx, double ly)
+{
+  if (!c || !phik_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_set_phik_dev: NULL argument");
+  if (!(lx > 0.0) || !(ly > 0.0)) return fail(EB_ERR_INVALID_ARGUMENT, "eb_set_phik_dev: lx, ly must be positive");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  EB_CUDA(cudaMemcpyAsync(c->d_phik, phik_dev, sizeof(double) * c->K, cudaMemcpyDeviceToDevice, c->stream));
+  c->lx = lx;
+  c->ly = ly;
+  return EB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kinematic models + forward RK4 (model_kernels.cuh), SURVEY.md section 8 row a8 / a9
+// ---------------------------------------------------------------------------
+static eb_status model_params(int model, const double* params, eb::ModelParams* m)
+{
+  if (model < 0 || model > 3) return fail(EB_ERR_INVALID_ARGUMENT, "unknown model (0 SimpleCart, 1 Omni, 2 Cart, 3 Mecanum)");
+  m->model = model;
+  m->a = m->b = m->c = 0.0;
+  if (model == eb::kModelCart || model == eb::kModelMecanum)
+  {
+    if (!params) return fail(EB_ERR_INVALID_ARGUMENT, "Cart / Mecanum need their wheel parameters");
+    m->a = params[0];
+    m->b = params[1];
+    m->c = model == eb::kModelMecanum ? params[2] : 0.0;
+  }
+  return EB_OK;
+}
+
+int eb_model_controls(int model) { return (model >= 0 && model <= 3) ? eb::model_controls(model) : 0; }
+
+eb_status eb_rk4_solve_dev(int device, int model, const double* params, double dt, double horizon, const double* x0_dev,
+                           const double* ut_dev, int per_instance, int count, double* xt_dev, int* fault_dev,
+                           void* cuda_stream)
+{
+  EB_TRACE("eb_rk4_solve_dev");
+  eb::ModelParams m{};
+  eb_status st = model_params(model, params, &m);
+  if (st != EB_OK) return st;
+  if (count < 0 || (count > 0 && (!x0_dev || !ut_dev || !xt_dev || !fault_dev)))
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_rk4_solve_dev: bad arguments");
+  if (!(dt != 0.0) || !std::isfinite(horizon / dt)) return fail(EB_ERR_INVALID_ARGUMENT, "eb_rk4_solve: dt must be non-zero");
+  const unsigned steps = static_cast<unsigned>(std::abs(horizon / dt));  // integrator.hpp:140
+  if (count == 0 || steps == 0) return EB_OK;
+  EB_CUDA(cudaSetDevice(device));
+  const long long stride = per_instance ? (long long)steps * eb::model_controls(model) : 0LL;
+  eb::rk4_solve_kernel<<<(count + 127) / 128, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      m, count, (int)steps, dt, x0_dev, ut_dev, stride, xt_dev, fault_dev);
+  EB_CUDA(cudaGetLastError());
+  return EB_OK;
+}
+
+eb_status eb_rk4_solve_host(int device, int model, const double* params, double dt, double horizon, const double* x0,
+                            const double* ut, int per_instance, int count, double* xt)
+{
+  if (count < 0 || (count > 0 && (!x0 || !ut || !xt))) return fail(EB_ERR_INVALID_ARGUMENT, "eb_rk4_solve_host: bad arguments");
+  if (!(dt != 0.0) || !std::isfinite(horizon / dt)) return fail(EB_ERR_INVALID_ARGUMENT, "eb_rk4_solve: dt must be non-zero");
+  const unsigned steps = static_cast<unsigned>(std::abs(horizon / dt));
+  if (count == 0 || steps == 0) return EB_OK;
+  if (model < 0 || model > 3) return fail(EB_ERR_INVALID_ARGUMENT, "unknown model (0 SimpleCart, 1 Omni, 2 Cart, 3 Mecanum)");
+  EB_CUDA(cudaSetDevice(device));
+  const int nu = eb::model_controls(model);
+  const size_t nut = (size_t)steps * nu * (per_instance ? (size_t)count : 1);
+  DevBuf dx, du, dxt;
+  int* d_fault = nullptr;
+  EB_CUDA(dx.alloc(3 * (size_t)count));
+  EB_CUDA(du.alloc(nut));
+  EB_CUDA(dxt.alloc(3 * (size_t)steps * count));
+  EB_CUDA(cudaMalloc(&d_fault, sizeof(int)));
+  cudaError_t e = cudaMemset(d_fault, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(dx.p, x0, sizeof(double) * 3 * count, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(du.p, ut, sizeof(double) * nut, cudaMemcpyHostToDevice);
+  eb_status st = EB_OK;
+  if (e == cudaSuccess) st = eb_rk4_solve_dev(device, model, params, dt, horizon, dx.p, du.p, per_instance, count, dxt.p, d_fault, nullptr);
+  int fault = 0;
+  if (e == cudaSuccess && st == EB_OK) e = cudaMemcpy(xt, dxt.p, sizeof(double) * 3 * (size_t)steps * count, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && st == EB_OK) e = cudaMemcpy(&fault, d_fault, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_fault);
+  if (st != EB_OK) return st;
+  if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_rk4_solve_host: ") + cudaGetErrorString(e));
+  if (fault) return fail(EB_ERR_INVALID_ARGUMENT, "Invalid twist y-velocity must be 0.");  // cart.hpp:169
+  return EB_OK;
+}
+
+eb_status eb_model_eval_host(int device, int model, const double* params, const double* x, const double* u, int count,
+                             double* f, double* A, double* B, double* vb)
+{
+  eb::ModelParams m{};
+  eb_status st = model_params(model, params, &m);
+  if (st != EB_OK) return st;
+  if (count < 1 || !x || !u) return fail(EB_ERR_INVALID_ARGUMENT, "eb_model_eval_host: bad arguments");
+  EB_CUDA(cudaSetDevice(device));
+  const int nu = eb::model_controls(model);
+  DevBuf dx, du, df, dA, dB, dv;
+  int* d_fault = nullptr;
+  EB_CUDA(dx.alloc(3 * (size_t)count));
+  EB_CUDA(du.alloc((size_t)nu * count));
+  EB_CUDA(df.alloc(3 * (size_t)count));
+  EB_CUDA(dA.alloc(9 * (size_t)count));
+  EB_CUDA(dB.alloc(3 * (size_t)nu * count));
+  EB_CUDA(dv.alloc(3 * (size_t)count));
+  EB_CUDA(cudaMalloc(&d_fault, sizeof(int)));
+  cudaError_t e = cudaMemset(d_fault, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(dx.p, x, sizeof(double) * 3 * count, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(du.p, u, sizeof(double) * nu * count, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+  {
+    eb::model_eval_kernel<<<(count + 127) / 128, 128>>>(m, count, dx.p, du.p, f ? df.p : nullptr, A ? dA.p : nullptr,
+                                                        B ? dB.p : nullptr, vb ? dv.p : nullptr, d_fault);
+    e = cudaGetLastError();
+  }
+  int fault = 0;
+  if (e == cudaSuccess && f) e = cudaMemcpy(f, df.p, sizeof(double) * 3 * count, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && A) e = cudaMemcpy(A, dA.p, sizeof(double) * 9 * count, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && B) e = cudaMemcpy(B, dB.p, sizeof(double) * 3 * nu * count, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && vb) e = cudaMemcpy(vb, dv.p, sizeof(double) * 3 * count, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(&fault, d_fault, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_fault);
+  if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_model_eval_host: ") + cudaGetErrorString(e));
+  if (fault) return fail(EB_ERR_INVALID_ARGUMENT, "Invalid twist y-velocity must be 0.");  // cart.hpp:169
+  return EB_OK;
+}
+
+// measured rate of random 1-byte loads over a 16 MB (L2-resident) buffer, in G sectors/s: the roofline
+// denominator of the collision / DynamicWindow kernels (every probe moves one 32-byte L2 sector)
+eb_status eb_l2_gather_peak(int device, double* gsectors_per_s)
+{
+  if (!gsectors_per_s) return fail(EB_ERR_INVALID_ARGUMENT, "eb_l2_gather_peak: NULL argument");
+  EB_CUDA(cudaSetDevice(device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const size_t bytes = 16u << 20;
+  unsigned char* buf = nullptr;
+  unsigned int* sink = nullptr;
+  EB_CUDA(cudaMalloc(&buf, bytes));
+  EB_CUDA(cudaMalloc(&sink, sizeof(unsigned int)));
+  cudaMemset(buf, 1, bytes);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  const int grid = sms * 8, threads = 256, iters = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++)
+  {
+    cudaEventRecord(a);
+    eb::l2_gather_probe<<<grid, threads>>>(buf, (unsigned int)(bytes - 1), iters, sink);
+    cudaEventRecord(b);
+    if (cudaEventSynchronize(b) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0) best = std::max(best, (double)grid * threads * iters * 8.0 / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(buf);
+  cudaFree(sink);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_l2_gather_peak: ") + cudaGetErrorString(e));
+  *gsectors_per_s = best;
+  return EB_OK;
 }
 
 eb_status eb_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops)

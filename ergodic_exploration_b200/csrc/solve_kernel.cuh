@@ -46,7 +46,16 @@ constexpr int kSolveWarps = EB_SOLVE_WARPS;  // warps (instances in flight) per 
 constexpr int kMaxPeers = 8;     // ranks of one NVSwitch box
 constexpr int kPeerBuffers = 4;  // gathered buffers rotating by step (fused gather)
 constexpr int kTabSlots = 16;    // time slots per coefficient chunk (half a round)
-constexpr int kGradPitch = 12;   // gradient tables: 8 slots + 4 pad, 12 % 16 -> conflict-free fragment loads
+constexpr int kGradPitch = 12;   // gradient x tables: 8 slots + 4 pad, 12 % 16 -> conflict-free fragment loads
+#ifndef EB_BANKFIX
+#define EB_BANKFIX 1
+#endif
+// y tables: pitch 8 puts consecutive rows 16 banks apart -> conflict-free LDS.128 of (t, t+1) pairs
+constexpr int kGradPitchY = EB_BANKFIX ? 8 : 12;
+// table stride: +8 doubles so the cos | sin tables written by one half-warp start 16 banks apart
+__host__ __device__ constexpr int grad_tab_stride(int nb) { return nb * kGradPitch + (EB_BANKFIX ? 8 : 0); }
+// S (NB x NB) in shared memory: pitch = 4 or 12 (mod 16) -> conflict-free A-fragment loads
+__host__ __device__ constexpr int s_pitch(int nb) { return (EB_BANKFIX && nb % 8 == 0) ? nb + 4 : nb; }
 constexpr int kTabStride = 20;   // 16 slots + 4 pad: 20 % 16 == 4 -> conflict-free fragment loads
 
 #ifdef EB_PHASE_TIMING
@@ -65,6 +74,34 @@ __device__ long long g_phase[65536 * kPhaseSlots];
 #ifdef EB_DEBUG_DUMP
 __device__ double g_dbg[4096 * 16];  // debug build only: per-step intermediates of instance 0
 #endif
+
+// Ablation timing (tools/ablate.sh; debug builds only, results are numerically WRONG): -DEB_ABL=<bits> removes a
+// class of work from the fused kernel so that its marginal cost can be read off the kernel time.
+//  1: c_k DMMAs -> integer xor of the operands   2: gradient DMMAs -> xor   4: c_k table recurrences + stores
+//  8: sin/cos polynomials -> 2 flops            16: gradient table recurrences + stores   64: warp scans -> identity
+#ifndef EB_ABL
+#define EB_ABL 0
+#endif
+__device__ __forceinline__ void abl_xor(double& d0, double a, double b)
+{
+  d0 = __hiloint2double(__double2hiint(d0), __double2loint(d0) ^ __double2loint(a) ^ __double2hiint(b));
+}
+__device__ __forceinline__ void dmma_ck(double& d0, double& d1, double a, double b)
+{
+#if EB_ABL & 1
+  abl_xor(d0, a, b);
+#else
+  dmma884(d0, d1, a, b);
+#endif
+}
+__device__ __forceinline__ void dmma_gr(double& d0, double& d1, double a, double b)
+{
+#if EB_ABL & 2
+  abl_xor(d0, a, b);
+#else
+  dmma884(d0, d1, a, b);
+#endif
+}
 
 struct SolveParams
 {
@@ -96,6 +133,53 @@ struct SolveParams
   const unsigned long long* my_flags;        // this rank's own arrival flags [n_peer] ...
   unsigned long long need;                   // ... must all have reached this before the buffer is reused
 };
+
+// The first twist of one instance: lanes 0..2 store one contiguous 24-byte segment (u0 may live in mapped host
+// memory); with a peer group (N > 1 GPUs) the same row goes into every rank's gathered buffer.
+__device__ __forceinline__ void publish_first_twist(const SolveParams& p, const int inst, const int lane, const double (&un)[3])
+{
+  const double a0 = __shfl_sync(kFull, un[0], 0), a1 = __shfl_sync(kFull, un[1], 0), a2 = __shfl_sync(kFull, un[2], 0);
+  const double mine = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+  if (lane < 3) p.u0[(size_t)inst * 3 + lane] = mine;
+  if (p.n_peer > 0)
+  {
+    // The gather IS these stores: the row goes straight into every rank's gathered
+    // buffer over NVLink (P2P stores, no separate collective, nothing to wait for
+    // on this rank).  When the last warp of the launch has published its row, this
+    // rank's arrival flag is raised on every peer (release at system scope).
+    // Buffer reuse: this step's buffer was last written kPeerBuffers steps ago; a rank
+    // reads a step's rows before it launches the next step, so once every rank has
+    // FINISHED step (this - kPeerBuffers + 1) -- p.need, long past in a balanced run --
+    // nobody can still be reading it.  Checked here, at the end of the warp's work.
+    if (lane < p.n_peer)
+      while (*(const volatile unsigned long long*)(p.my_flags + lane) < p.need) __nanosleep(100);
+    __syncwarp();
+    if (lane < 3)
+    {
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; q++)
+        if (q < p.n_peer) p.u0_peer[q][(size_t)inst * 3 + lane] = mine;
+    }
+    // release at GPU scope into the arrival counter; the last warp's system-scope fence is
+    // cumulative over every row it has thereby observed (PTX memory model: the gpu-scope
+    // fence + counter increment of each warp synchronises with the last warp's read of the
+    // counter, and causality order is transitive), so only that one warp pays for a system fence
+    __threadfence();
+    __syncwarp();
+    if (lane == 0)
+    {
+      const unsigned int prev = atomicAdd(p.done_counter, 1u);
+      if (prev == (unsigned int)p.B - 1u)
+      {
+        *p.done_counter = 0u;  // ready for the next launch on this stream
+        __threadfence_system();
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; q++)
+          if (q < p.n_peer) *(volatile unsigned long long*)p.flag_peer[q] = p.flag_value;
+      }
+    }
+  }
+}
 
 template <int MODEL>
 __device__ __forceinline__ void model_f(double u0, double u1, double c, double s, double& fx, double& fy)
@@ -191,6 +275,9 @@ __device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, const int
       double em = ok ? fma(2.0 * v, v, -1.0) : 0.0, ek = ok ? 1.0 : 0.0;
       double om = ok ? v : 0.0, ok1 = om;
       __syncwarp();  // the previous half's fragment loads are done
+#if EB_ABL & 4
+      mytab[0] = ek + ok1 + em * m;
+#else
 #pragma unroll
       for (int k = 0; k < NB; k += 2)
       {
@@ -202,6 +289,7 @@ __device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, const int
         om = ok1;
         ok1 = on;
       }
+#endif
     }
     __syncwarp();
     const int ksteps = (min(left, kTabSlots) + 3) >> 2;
@@ -219,7 +307,7 @@ __device__ __forceinline__ void coeff_chunk(double* __restrict__ tabx, const int
 #pragma unroll
       for (int ti = 0; ti < TILES; ti++)
 #pragma unroll
-        for (int tj = 0; tj < TILES; tj++) dmma884(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
+        for (int tj = 0; tj < TILES; tj++) dmma_ck(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
     }
   }
 }
@@ -264,7 +352,8 @@ struct SolveCfg
   static constexpr bool kDmmaGrad = EB_DMMA_GRAD && (NB == 16 || NB == 20 || NB == 24 || (EB_DMMA_GRAD_SMALL && NB <= 12));
   // per-warp table region: the two c_k tables (pitch 20, 16 slots) or the four gradient
   // tables (pitch 12, 8 slots), whichever is larger; S (NB x NB) aliases it
-  static constexpr int kTabDoubles = kDmmaGrad ? 4 * NB * kGradPitch : 2 * NB * kTabStride;
+  static constexpr int kSPitch = kDmmaGrad ? s_pitch(NB) : NB;
+  static constexpr int kTabDoubles = kDmmaGrad ? (4 * grad_tab_stride(NB) > NB * kSPitch ? 4 * grad_tab_stride(NB) : NB * kSPitch) : 2 * NB * kTabStride;
   static constexpr int kBlock = NB <= 12 ? NB : (NB == 20 ? EB_KB_20 : NB == 16 ? EB_KB_16 : 8);
   static constexpr int kMinBlocks =
       (NB <= 10 ? EB_MINB_10 : NB <= 12 ? 6 : NB <= 16 ? EB_MINB_16 : NB <= 24 ? EB_MINB_20 : 4) * 4 / kSolveWarps;
@@ -319,6 +408,11 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
         const uint64_t r = mix64(mix64(p.seed + p.call * 0xD1B54A32D192ED03ull) ^
                                  ((uint64_t)inst * 0x9E3779B97F4A7C15ull + (uint64_t)j));
         idx = (long long)__umul64hi(r, (uint64_t)p.mem_count);
+      }
+      if ((unsigned long long)idx >= (unsigned long long)p.mem_count)
+      {  // buffer.cpp:84,103: memory_.at() throws; here: fault bit 2 (-> EB_ERR_OUT_OF_RANGE) and a safe index
+        atomicOr(p.fault, 2);
+        idx = 0;
       }
       if (p.idx_mode != 0 && p.mem_idx_out) p.mem_idx_out[(size_t)inst * p.batch_size + j] = (int)idx;
       const double* h = p.hist + ((size_t)idx * p.B + inst) * 3;
@@ -410,7 +504,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
             metric += s * d;
             if (p.ck) p.ck[(size_t)inst * K + k] = c;
           }
-          if (ky < NB && kx < NB) Ssm[ky * NB + kx] = s;
+          if (ky < NB && kx < NB) Ssm[ky * Cfg::kSPitch + kx] = s;
         }
     if (p.metric)
     {
@@ -443,7 +537,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
       for (int ks = 0; ks < GKS; ks++)
       {
         const int ky = 8 * mi + g, kx = 4 * ks + q;
-        const double sv = (ky < NB && kx < NB) ? Ssm[ky * NB + kx] : 0.0;
+        const double sv = (ky < NB && kx < NB) ? Ssm[ky * Cfg::kSPitch + kx] : 0.0;
         SA[mi][ks] = sv * ((double)kx * p.ax);
         SB[mi][ks] = sv * ((double)ky * p.by);
       }
@@ -476,14 +570,16 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
       const int g = lane >> 2, q = lane & 3;
       const int axis = lane >> 4, chain = (lane >> 3) & 1, slot = lane & 7;
       double* const gt = tabx;  // [axis][chain][k][12]: cos(kx a x) | sin(kx a x) | cos(ky b y) | sin(ky b y)
-      double* const mytab = gt + (axis * 2 + chain) * (NB * kGradPitch) + slot;
+      constexpr int TS = grad_tab_stride(NB);
+      const int mypitch = axis ? kGradPitchY : kGradPitch;
+      double* const mytab = gt + (axis * 2 + chain) * TS + slot;
       const double* const txc = gt;
-      const double* const txs = gt + NB * kGradPitch;
-      const double* const tyc = gt + 2 * NB * kGradPitch;
-      const double* const tys = gt + 3 * NB * kGradPitch;
+      const double* const txs = gt + TS;
+      const double* const tyc = gt + 2 * TS;
+      const double* const tys = gt + 3 * TS;
       // e_x / e_y of the round's 32 steps are handed to the time-step lanes through the pad
       // slots (8..11) of rows 0..7 of the first two tables
-      auto stage = [&](int which, int t) { return gt + which * (NB * kGradPitch) + (t >> 2) * kGradPitch + 8 + (t & 3); };
+      auto stage = [&](int which, int t) { return gt + which * TS + (t >> 2) * kGradPitch + 8 + (t & 3); };
       const int left = p.N - r * 32;  // valid steps in this round (warp-uniform)
       const int ntiles = min(4, (left + 7) >> 3);
       for (int nj = 0; nj < ntiles; nj++)
@@ -512,17 +608,21 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
         }
         if (!ok) em = ek = om = ok1 = 0.0;
         __syncwarp();  // the previous tile's fragment / staging traffic is done
+#if EB_ABL & 16
+        mytab[0] = ek + ok1 + em * m;
+#else
 #pragma unroll
         for (int k = 0; k < NB; k += 2)
         {
-          mytab[k * kGradPitch] = ek;
-          mytab[(k + 1) * kGradPitch] = ok1;
+          mytab[k * mypitch] = ek;
+          mytab[(k + 1) * mypitch] = ok1;
           const double en = fma(m, ek, -em), on = fma(m, ok1, -om);
           em = ek;
           ek = en;
           om = ok1;
           ok1 = on;
         }
+#endif
         __syncwarp();
         double R1[TILES][2], R2[TILES][2];
 #pragma unroll
@@ -537,8 +637,8 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
 #pragma unroll
           for (int mi = 0; mi < TILES; mi++)
           {
-            dmma884(R1[mi][0], R1[mi][1], SA[mi][ks], bs);
-            dmma884(R2[mi][0], R2[mi][1], SB[mi][ks], bc);
+            dmma_gr(R1[mi][0], R1[mi][1], SA[mi][ks], bs);
+            dmma_gr(R2[mi][0], R2[mi][1], SB[mi][ks], bc);
           }
         }
         // lane (g, q) holds R[ky = 8 mi + g][slot 2q, 2q + 1]: weight with the y tables
@@ -549,8 +649,8 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
           const int ky = 8 * mi + g;
           if ((TILES * 8 == NB) || (ky < NB))
           {
-            const double2 cy2 = *reinterpret_cast<const double2*>(tyc + ky * kGradPitch + 2 * q);
-            const double2 sy2 = *reinterpret_cast<const double2*>(tys + ky * kGradPitch + 2 * q);
+            const double2 cy2 = *reinterpret_cast<const double2*>(tyc + ky * kGradPitchY + 2 * q);
+            const double2 sy2 = *reinterpret_cast<const double2*>(tys + ky * kGradPitchY + 2 * q);
             v0 = fma(cy2.x, R1[mi][0], v0);
             v1 = fma(cy2.y, R1[mi][1], v1);
             w0 = fma(sy2.x, R2[mi][0], w0);
@@ -604,7 +704,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
         for (int ky = 0; ky < NB; ky++)
         {
           double rx0 = 0.0, rx1 = 0.0, ry0 = 0.0, ry1 = 0.0;
-          const double* srow = Ssm + ky * NB + kb;
+          const double* srow = Ssm + ky * Cfg::kSPitch + kb;
 #pragma unroll
           for (int j = 0; j < KB; j += 2)
           {
@@ -697,52 +797,17 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
       bt1 = 0.0;
     }
     double un[3];
+    bool finite = true;
 #pragma unroll
     for (int c = 0; c < 3; c++)
     {
       const double v = -((p.Rinv[c + 0] * bt0 + p.Rinv[c + 3] * bt1) + p.Rinv[c + 6] * r2);
+      finite &= fabs(v) <= 1.7976931348623157e308;  // false for NaN and Inf
       un[c] = clampd(v, p.umin[c], p.umax[c]);
       if (valid) ut_out[i * 3 + c] = un[c];
     }
-    if (r == 0)
-    {
-      // first twist: lanes 0..2 store one contiguous 24-byte segment (u0 may live in mapped host memory)
-      const double a0 = __shfl_sync(kFull, un[0], 0), a1 = __shfl_sync(kFull, un[1], 0),
-                   a2 = __shfl_sync(kFull, un[2], 0);
-      const double mine = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
-      if (lane < 3) p.u0[(size_t)inst * 3 + lane] = mine;
-      if (p.n_peer > 0)
-      {
-        // The gather IS these stores: the row goes straight into every rank's gathered
-        // buffer over NVLink (P2P stores, no separate collective, nothing to wait for
-        // on this rank).  When the last warp of the launch has published its row, this
-        // rank's arrival flag is raised on every peer (release at system scope).
-        // Buffer reuse: this step's buffer was last written kPeerBuffers steps ago; a rank
-        // reads a step's rows before it launches the next step, so once every rank has
-        // FINISHED step (this - kPeerBuffers + 1) -- p.need, long past in a balanced run --
-        // nobody can still be reading it.  Checked here, at the end of the warp's work.
-        if (lane < p.n_peer)
-          while (*(const volatile unsigned long long*)(p.my_flags + lane) < p.need) __nanosleep(100);
-        __syncwarp();
-        if (lane < 3)
-          for (int q = 0; q < p.n_peer; q++) p.u0_peer[q][(size_t)inst * 3 + lane] = mine;
-        // release at GPU scope into the arrival counter; the last warp's system-scope fence is
-        // cumulative over every row it has thereby observed (PTX memory model), so only that
-        // one warp pays for a system fence
-        __threadfence();
-        __syncwarp();
-        if (lane == 0)
-        {
-          const unsigned int prev = atomicAdd(p.done_counter, 1u);
-          if (prev == (unsigned int)p.B - 1u)
-          {
-            *p.done_counter = 0u;  // ready for the next launch on this stream
-            __threadfence_system();
-            for (int q = 0; q < p.n_peer; q++) *(volatile unsigned long long*)p.flag_peer[q] = p.flag_value;
-          }
-        }
-      }
-    }
+    if (valid && !finite) atomicOr(p.fault, 4);  // NaN / Inf guard
+    if (r == 0) publish_first_twist(p, inst, lane, un);
   }
   EB_PHASE(4);
 #ifdef EB_PHASE_TIMING

@@ -99,6 +99,20 @@ class ShardedErgodicControl:
         return all_gather_rows(u0, self.total, self.group)
 
 
+FUSE_MIN_BATCH_DEFAULT = 8192  # keep in step with eb_peer_group::fuse_min_batch (csrc/ergodic_b200.cu)
+
+
+def gather_mode_for_batch(batch: int) -> str:
+    """which branch of eb_control_dev_gather publishes a batch of this size"""
+    import os
+    thr = int(os.environ.get("EB_GATHER_FUSE_MIN_BATCH", FUSE_MIN_BATCH_DEFAULT))
+    if batch >= thr:
+        return ("fused into the solve kernel: every warp stores its row into all ranks' gathered buffers "
+                "(P2P stores over NVLink peer memory), arrival flags raised by the launch's last warp")
+    return ("solve kernel writes u0 locally, peer_publish_kernel on the group's side stream copies the block to all "
+            "ranks over NVLink peer memory and raises the arrival flags")
+
+
 class _DevView:
     """zero-copy torch view of device memory owned by the C library"""
 
@@ -120,6 +134,15 @@ class PeerGather:
         multi = dist.is_initialized() and dist.get_world_size(group) > 1
         self.world = dist.get_world_size(group) if multi else 1
         self.rank = dist.get_rank(group) if multi else 0
+        if multi:
+            # every rank's row block starts at rank * 3 * batch in every gathered buffer: the batches must be
+            # equal, or ranks would store over each other's rows (and past the end of the smaller buffers)
+            dev0 = torch.device("cuda", ctl.device)
+            mm = torch.tensor([ctl.batch, -ctl.batch], dtype=torch.int64, device=dev0)
+            dist.all_reduce(mm, op=dist.ReduceOp.MIN, group=group)
+            if int(mm[0].item()) != -int(mm[1].item()):
+                raise ValueError(f"PeerGather needs the same batch on every rank (min {int(mm[0].item())}, "
+                                 f"max {-int(mm[1].item())}); pad the smaller shards or use all_gather_rows")
         h = C.c_void_p()
         check(self._lib.eb_peer_group_create(ctl.device, self.rank, self.world, 3 * ctl.batch, C.byref(h)))
         self._h = h
@@ -154,12 +177,23 @@ class PeerGather:
             self._h = None
 
     def __del__(self):
+        # Without the barrier of close() a peer may still be storing into buffers freed here: with more than
+        # one rank the group is deliberately leaked (and reported) instead of destroyed behind the peers' backs.
         try:
             if getattr(self, "_h", None):
-                self._lib.eb_peer_group_destroy(self._h)
+                if self.world > 1:
+                    import warnings
+                    warnings.warn("PeerGather dropped without close(): peer-mapped buffers are left allocated",
+                                  ResourceWarning)
+                else:
+                    self._lib.eb_peer_group_destroy(self._h)
                 self._h = None
         except Exception:
             pass
+
+    def mode(self) -> str:
+        """the publication branch eb_control_dev_gather takes for this controller's batch"""
+        return gather_mode_for_batch(self.ctl.batch)
 
     @property
     def steps(self) -> int:

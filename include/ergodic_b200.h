@@ -56,6 +56,8 @@ typedef enum eb_model {
 
 /* Constructor arguments of ErgodicControl (ergodic_control.hpp:90-94) plus
  * the two constants the reference hard-codes in gradBarrier (:457-458). */
+/* DEVIATION: num_basis is limited to 1..32 (the reference accepts any count, basis.cpp:48-77): the coefficient block
+ * of one instance lives in the registers of one warp.  eb_create returns EB_ERR_INVALID_ARGUMENT beyond that. */
 typedef struct eb_config {
   int model;            /* eb_model */
   int batch;            /* B >= 1 independent instances */
@@ -176,6 +178,10 @@ eb_status eb_phik_plan_create(int device, int nx, int ny, double resolution, dou
  * + one all-reduce(sum) of the 1024 raw values, then divide by raw[0]. */
 eb_status eb_phik_plan_create_rows(int device, int nx, int ny_total, int row_begin, int row_count,
                                    double resolution, double lx, double ly, int nb, eb_phik_plan **out);
+/* as eb_phik_plan_create_rows with the grid's first sample point at (x_first, y_first) instead of (0, 0): the
+ * coordinates are x_first + accumulated j * resolution (cell CENTRES of an occupancy grid: x_first = resolution / 2) */
+eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin, int row_count, double resolution,
+                                 double lx, double ly, int nb, double x_first, double y_first, eb_phik_plan **out);
 void eb_phik_plan_destroy(eb_phik_plan *p);
 eb_status eb_phik_plan_set_stream(eb_phik_plan *p, void *cuda_stream);
 /* algo: 0 = auto, 1 = simple (any shape), 2 = DMMA tiles (TMA-fed; mirror-folded when the
@@ -238,6 +244,11 @@ eb_status eb_control_dev_gather(eb_controller *c, eb_peer_group *g, double xmin,
 eb_status eb_peer_group_wait(eb_peer_group *g, eb_controller *c, unsigned long long step);
 double *eb_peer_gathered_dev(eb_peer_group *g, unsigned long long step);
 unsigned long long eb_peer_group_steps(const eb_peer_group *g);
+/* 1: a batch of this size publishes from inside the solve kernel, 0: from the group's side stream */
+int eb_peer_group_fused(const eb_peer_group *g, int batch);
+/* NOTE (equal shards): every rank's row block starts at rank * elems_per_rank in every gathered buffer, so all
+ * ranks of a group MUST be created with the same elems_per_rank (= 3 * batch); uneven shards have to be padded
+ * by the caller (the Python PeerGather checks this with one all_reduce at construction). */
 
 /* ---- occupancy-grid collision checks ----------------
  * Batched Collision::collisionCheck (collision.cpp:126-143) and validate_control
@@ -307,7 +318,48 @@ eb_status eb_dwa_control_traj_dev(eb_grid *g, const eb_collision *c, const eb_dw
                                   const double *vb_dev, const double *xt_ref_dev, int ncols, int per_instance,
                                   double dt_ref, int count, int *found_dev, double *u_opt_dev, double *min_cost_dev);
 
-/* ---- measurement helper --------------------------------------------------
+/* ---- map-derived target ------------------------------
+ * Density from an occupancy grid: Phi[i][j] = entropy(cell / 100) (numerics.hpp:164-179 over GridMap::getCell,
+ * grid.cpp:177-184; -1 = unknown), sampled at the cell centres of the map frame [0, xsize * res] x [0, ysize * res],
+ * normalised like Target::fill (target.cpp:87) and contracted like Basis::spatialCoeff (basis.cpp:122-133).
+ * One execute per map update; phik_dev can be handed to eb_set_phik_dev without a host round trip. */
+typedef struct eb_map_target eb_map_target;
+eb_status eb_map_target_create(int device, unsigned int xsize, unsigned int ysize, double resolution, int nb,
+                               eb_map_target **out);
+void eb_map_target_destroy(eb_map_target *m);
+eb_status eb_map_target_set_stream(eb_map_target *m, void *cuda_stream);
+eb_status eb_map_target_execute_dev(eb_map_target *m, const signed char *cells_dev, double *phik_dev,
+                                    double *phi_sum_dev /* may be NULL */);
+eb_status eb_map_target_execute_host(eb_map_target *m, const signed char *cells, double *phik, double *phi_sum);
+double *eb_map_target_density_dev(eb_map_target *m); /* un-normalised entropy density of the last execute, [ysize][xsize] */
+eb_status eb_map_target_extent(const eb_map_target *m, double *lx, double *ly);
+long long eb_map_target_launch_count(const eb_map_target *m);
+/* phik_ <- a device buffer of K doubles (stream-ordered copy), basis extent (lx, ly) */
+eb_status eb_set_phik_dev(eb_controller *c, const double *phik_dev, double lx, double ly);
+
+/* ---- kinematic models and the forward integrator ----
+ * model: 0 SimpleCart, 1 Omni (models/cart.hpp:152-206, models/omni.hpp:164-215), 2 Cart (cart.hpp:60-145;
+ * params = { wheel_radius, wheel_base }; 2 wheel velocities), 3 Mecanum (omni.hpp:59-157; params = { wheel_radius,
+ * wheel_base_x, wheel_base_y }; 4 wheel velocities).  eb_rk4_solve = RungeKutta::solve (integrator.hpp:135-152):
+ * x0 3 x count, ut nu x steps (one signal for all instances) or nu x steps x count (per_instance), xt 3 x steps x count,
+ * steps = |horizon / dt|, heading wrapped after every step.  SimpleCart with a y-velocity: EB_ERR_INVALID_ARGUMENT
+ * (cart.hpp:167-170) from the _host call, bit 0 of *fault_dev from the _dev call. */
+int eb_model_controls(int model);
+eb_status eb_rk4_solve_host(int device, int model, const double *params, double dt, double horizon, const double *x0,
+                            const double *ut, int per_instance, int count, double *xt);
+eb_status eb_rk4_solve_dev(int device, int model, const double *params, double dt, double horizon,
+                           const double *x0_dev, const double *ut_dev, int per_instance, int count, double *xt_dev,
+                           int *fault_dev, void *cuda_stream);
+/* operator() -> f (3 x count), fdx -> A (3 x 3 x count), fdu -> B (3 x nu x count), wheels2Twist -> vb (3 x count);
+ * outputs may be NULL */
+eb_status eb_model_eval_host(int device, int model, const double *params, const double *x, const double *u, int count,
+                             double *f, double *A, double *B, double *vb);
+
+/* ---- measurement helpers --------------------------------------------------
+ * eb_l2_gather_peak: measured rate (G sectors/s) of random 1-byte loads over a 16 MB L2-resident buffer -- the
+ * roofline denominator of the collision / DynamicWindow kernels. */
+eb_status eb_l2_gather_peak(int device, double *gsectors_per_s);
+/*
  * Measured FP64 throughput of the device (TFLOP/s, 2 flop per FMA): a
  * register-resident DFMA loop and an mma.sync m8n8k4 f64 (DMMA) loop.  Used
  * as the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 figure). */

@@ -433,6 +433,38 @@ int eo_rk4_forward_cart(double wheel_radius, double wheel_base, double dt, doubl
   return rk4_forward(dyn_cart, &c, 2, dt, horizon, x0, ut, xt);
 }
 
+struct mecanum_ctx {
+  double r, bx, by;
+};
+static int dyn_mecanum(const void *ctx, const double x[3], const double *u, double xdot[3])
+{
+  const struct mecanum_ctx *c = (const struct mecanum_ctx *)ctx;
+  eo_mecanum_f(c->r, c->bx, c->by, x, u, xdot);
+  return 0;
+}
+
+/* RungeKutta::solve fwd for models::Mecanum (omni.hpp:59-157), 4 wheel velocities per step */
+int eo_rk4_forward_mecanum(double r, double bx, double by, double dt, double horizon, const double x0[3],
+                           const double *ut, double *xt)
+{
+  struct mecanum_ctx c = { r, bx, by };
+  return rk4_forward(dyn_mecanum, &c, 4, dt, horizon, x0, ut, xt);
+}
+
+/* entropy of one cell, numerics.hpp:164-179 */
+double eo_entropy(double p)
+{
+  if (eo_almost_equal(0.0, p, 1.0e-12) || eo_almost_equal(1.0, p, 1.0e-12)) return 1e-3;
+  else if (p < 0.0) return 0.7;
+  return -p * log(p) - (1.0 - p) * log(1.0 - p);
+}
+
+/* entropy of every cell of an occupancy grid: p = GridMap::getCell = int8 / 100 (grid.cpp:177-184) */
+void eo_entropy_grid(const signed char *cells, long long n, double *out)
+{
+  for (long long i = 0; i < n; i++) out[i] = eo_entropy((double)cells[i] / 100.0);
+}
+
 /* rhodot ergodic_control.hpp:65-69: -gdx - dbar - fdx.t()*rho */
 static void rhodot(const double rho[3], const double gdx[3], const double dbar[3],
                    const double A[9], double out[3])

@@ -69,6 +69,10 @@ int eo_rk4_forward_cart(double wheel_radius, double wheel_base, double dt,
                         double horizon, const double x0[3], const double *ut,
                         double *xt);
 /* RungeKutta::solve bwd :154-174 (+step :186-194, rhodot ergodic_control.hpp:65-69) */
+int eo_rk4_forward_mecanum(double r, double bx, double by, double dt, double horizon,
+                           const double x0[3], const double *ut /*4 x steps*/, double *xt);
+double eo_entropy(double p);                                       /* numerics.hpp:164-179 */
+void eo_entropy_grid(const signed char *cells, long long n, double *out); /* + grid.cpp:177-184 */
 void eo_rk4_backward(int model, double dt, int steps, const double rhoT[3],
                      const double *xt, const double *ut, const double *edx,
                      const double *bdx, double *rhot);

@@ -172,6 +172,25 @@ int ref_rk4_forward_cart(double r, double b, double dt, double horizon, const do
   return int(steps);
 }
 
+int ref_rk4_forward_mecanum(double r, double bx, double by, double dt, double horizon, const double* x0,
+                            const double* ut, double* xt)
+{
+  const unsigned steps = static_cast<unsigned>(std::abs(horizon / dt));
+  mat u(4, steps);
+  std::memcpy(u.memptr(), ut, sizeof(double) * 4 * steps);
+  const ee::RungeKutta rk(dt);
+  out_mat(rk.solve(ee::models::Mecanum(r, bx, by), v3(x0), u, horizon), xt);
+  return int(steps);
+}
+double ref_entropy(double p) { return ee::entropy(p); }
+// entropy(getCell(idx)) for every cell of a GridMap built from the raw int8 data (grid.cpp:177-184, numerics.hpp:164-179)
+void ref_entropy_grid(const signed char* data, unsigned xsize, unsigned ysize, double res, double* out)
+{
+  const std::vector<int8_t> cells(data, data + (size_t)xsize * ysize);
+  const ee::GridMap grid(0.0, xsize * res, 0.0, ysize * res, res, cells);
+  for (unsigned i = 0; i < xsize * ysize; i++) out[i] = ee::entropy(grid.getCell(i));
+}
+
 // ---- basis / target -------------------------------------------------------
 void ref_basis_tables(int nb, long long* k, double* lamdak)
 {
