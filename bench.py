@@ -657,14 +657,10 @@ def bench_phik(ctx, steps, warmup, with_cpu=True):
     nb, res = 32, 0.1
     lx = ly = (nx - 1) * res
     lo, hi = shard_bounds(ny, world, rank)
-    g = torch.Generator(device=ctx.dev).manual_seed(0xE16C0D1C + 3)
-    xs = torch.arange(nx, device=ctx.dev, dtype=torch.float64) * res
-    ys = torch.arange(lo, hi, device=ctx.dev, dtype=torch.float64) * res
-    phi = torch.zeros((hi - lo, nx), dtype=torch.float64, device=ctx.dev)
-    for _ in range(8):  # un-normalised mixture of 8 Gaussians; same stream on every rank
-        mu = (0.1 + 0.8 * torch.rand(2, generator=g, device=ctx.dev, dtype=torch.float64)) * lx
-        sg = (0.02 + 0.08 * torch.rand(2, generator=g, device=ctx.dev, dtype=torch.float64)) * lx
-        phi += torch.exp(-0.5 * ((xs[None, :] - mu[0]) / sg[0]) ** 2 - 0.5 * ((ys[:, None] - mu[1]) / sg[1]) ** 2)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from c3_density import c3_density_torch  # un-normalised mixture of 8 Gaussians, closed form
+
+    phi = c3_density_torch(ctx.dev, nx, res, lo, hi)
     algo = int(os.environ.get("EB_PHIK_ALGO", "0"))
     plan = eb.PhikPlan(nx, hi - lo, res, lx, ly, nb, device=ctx.local_rank, algo=algo, row_begin=lo, ny_total=ny)
     fold, fold_dev = plan.fold()
@@ -702,7 +698,8 @@ def bench_phik(ctx, steps, warmup, with_cpu=True):
         want = np.load(gpath)["phik"]
         got = step().cpu().numpy()
         parity = {"max_rel_err_vs_golden": float(np.max(np.abs(got - want)) / np.max(np.abs(want))), "tolerance": 1e-9,
-                  "golden": "tests/golden/c3_phik_8192.npz (CPU oracle, long double accumulation)"}
+                  "golden": "tests/golden/c3_phik_8192.npz (CPU oracle eo_phik_rows over the same closed-form density, "
+                            "tests/golden/make_golden_c3.py)"}
 
     # end to end (N = 1): pinned host density in, phi_k out, through eb_phik_execute_host
     e2e = None
@@ -927,6 +924,54 @@ def bench_avoid(ctx, mode, steps, warmup):
     return res_d
 
 
+def peer_stress(ctx, steps=48):
+    """N > 1, untimed: the flag / fence protocol of the fused gather under skew.  Both publication branches (a
+    single-wave batch on the side stream, a multi-wave batch from inside the solve kernel); every step ONE rank is
+    held back by a ~1 ms spin kernel and NO collective runs between steps, so the fast ranks run ahead until the
+    4-buffer reuse guard stops them.  Every step's gathered block is copied after its wait; at the end the copies
+    must equal an NCCL all_gather of the ranks' own rows, bit for bit, on every rank."""
+    torch, dist, eb = ctx.torch, ctx.dist, ctx.eb
+    from ergodic_exploration_b200.sharding import PeerGather
+
+    world, rank = ctx.world, ctx.rank
+    results = {}
+    for name, B in (("side_stream", 1024), ("in_kernel", 40000)):
+        wl = WORKLOADS["c2"]
+        R, umin, umax = model_params(wl["model"])
+        x, ut, _ = synth_inputs(wl, B, seed=0xE16C0D1C + 40 + rank)
+        ctl = eb.ErgodicControl(wl["model"], DT, wl["horizon"], 0.1, 1.0, wl["nb"], 1000, 100, R, umin, umax, batch=B,
+                                device=ctx.local_rank)
+        ctl.setTarget([eb.Gaussian(m, s) for m, s in zip(MU, SIGMA)])
+        ctl.set_ut(ut)
+        ctl.keep_ck(False)
+        xd = torch.from_numpy(x).to(ctx.dev)
+        pg = PeerGather(ctl)
+        mine = torch.empty((steps, B, 3), dtype=torch.float64, device=ctx.dev)
+        seen = torch.empty((steps, world * B, 3), dtype=torch.float64, device=ctx.dev)
+        ctx.barrier()
+        for s_ in range(steps):
+            if s_ % world == rank:
+                torch.cuda._sleep(2_000_000)  # ~1 ms: this rank falls behind
+            st = pg.control(BOUNDS, xd)
+            pg.wait(st)
+            g = pg.gathered(st)
+            seen[s_].copy_(g)
+            mine[s_].copy_(g[rank * B:(rank + 1) * B])
+        ctl.check()
+        ctx.barrier()
+        allm = torch.empty((world, steps, B, 3), dtype=torch.float64, device=ctx.dev)
+        dist.all_gather_into_tensor(allm, mine)
+        want = allm.permute(1, 0, 2, 3).reshape(steps, world * B, 3)
+        ok = torch.tensor([1 if torch.equal(want, seen) else 0], dtype=torch.int32, device=ctx.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        results[name] = {"batch_per_gpu": B, "steps": steps, "branch": pg.mode()[:40], "bit_identical_on_all_ranks": bool(ok.item())}
+        pg.close()
+        ctl.close()
+        if not ok.item():
+            raise SystemExit(f"bench.py: peer gather stress ({name}) disagrees with NCCL all_gather")
+    return results
+
+
 def primary_line(res):
     """the driver's contract: the primary workload's result at the top level of the JSON line"""
     line = {k: res[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
@@ -962,8 +1007,11 @@ def run_ours(args):
             r = {"workload": key, "error": f"{type(exc).__name__}: {exc}"} if ctx.rank == 0 else None
         results.append(r)
         ctx.torch.cuda.empty_cache()
+    stress = peer_stress(ctx) if (ctx.world > 1 and args.workload == "all") else None
     if ctx.rank == 0:
         line = primary_line(results[0])
+        if stress is not None:
+            line["peer_stress"] = stress
         if len(results) > 1:
             line["secondary"] = [r for r in results[1:] if r is not None]
             line["clocks_all_timed_regions"] = ctx.clocks.summary(None)

@@ -27,6 +27,7 @@
 #include "peer_gather.cuh"
 #include "phik_dmma.cuh"
 #include "phik_kernels.cuh"
+#include "phik_tma.cuh"
 #include "solve_kernel.cuh"
 #include "solve_kernel_v2.cuh"
 
@@ -102,11 +103,13 @@ struct eb_phik_plan
   double *d_cx = nullptr, *d_cy = nullptr;  // cosine tables [n][32]
   double* d_cxp = nullptr;                  // C_x re-laid for the DMMA tile kernel
   double* d_cxpf = nullptr;                 // ... for the mirror-folded tile kernel (left half, even | odd orders)
+  double *d_cxt = nullptr, *d_cxtf = nullptr;  // C_x re-laid for the TMA tile kernel (phik_tma.cuh), unfolded / folded
   bool fold = false;                        // the grid's cosine tables are mirror-symmetric to <= kFoldTol
   double fold_dev = 0.0;                    // measured max |C_x[j][k] - (-1)^k C_x[nx-1-j][k]|
   double *d_T = nullptr;                    // stage-1 result [ny][32]
   double *d_parts = nullptr;                // partial 32x32 blocks
   double *d_phik = nullptr, *d_sum = nullptr;  // staging for the _host call
+  unsigned int* d_done = nullptr;              // arrival counter of the TMA kernel's fused final sum
   int max_parts = 0;
   long long launches = 0;
 };
@@ -217,6 +220,8 @@ eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin
   EB_CUDA_P(cudaMalloc(&p->d_parts, sizeof(double) * 1024 * (size_t)p->max_parts));
   EB_CUDA_P(cudaMalloc(&p->d_phik, sizeof(double) * 1024));
   EB_CUDA_P(cudaMalloc(&p->d_sum, sizeof(double)));
+  EB_CUDA_P(cudaMalloc(&p->d_done, sizeof(unsigned int)));
+  EB_CUDA_P(cudaMemset(p->d_done, 0, sizeof(unsigned int)));
   EB_CUDA_P(cudaMemcpy(p->d_xs, xs.data(), sizeof(double) * nx, cudaMemcpyHostToDevice));
   EB_CUDA_P(cudaMemcpy(p->d_ys, ys.data(), sizeof(double) * ny, cudaMemcpyHostToDevice));
   // basis.cpp:85: cos(k * (PI / l) * x)
@@ -253,6 +258,20 @@ eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin
       }
     }
   }
+  if (eb::phik_tma_supported(nx, ny))
+  {
+    const int rows_u = eb::phik_tma_cx_rows(nx, false);
+    EB_CUDA_P(cudaMalloc(&p->d_cxt, sizeof(double) * (size_t)rows_u * eb::kPdPitch));
+    eb::phik_tma_permute_cx<<<(rows_u * eb::kPdPitch + 255) / 256, 256>>>(p->d_cx, nx, rows_u, 0, p->d_cxt);
+    p->launches += 1;
+    if (p->fold)
+    {
+      const int rows_f = eb::phik_tma_cx_rows(nx / 2, true);
+      EB_CUDA_P(cudaMalloc(&p->d_cxtf, sizeof(double) * (size_t)rows_f * eb::kPdPitch));
+      eb::phik_tma_permute_cx<<<(rows_f * eb::kPdPitch + 255) / 256, 256>>>(p->d_cx, nx / 2, rows_f, 1, p->d_cxtf);
+      p->launches += 1;
+    }
+  }
   EB_CUDA_P(cudaGetLastError());
   EB_CUDA_P(cudaDeviceSynchronize());
 #undef EB_CUDA_P
@@ -270,10 +289,13 @@ void eb_phik_plan_destroy(eb_phik_plan* p)
   cudaFree(p->d_cy);
   cudaFree(p->d_cxp);
   cudaFree(p->d_cxpf);
+  cudaFree(p->d_cxt);
+  cudaFree(p->d_cxtf);
   cudaFree(p->d_T);
   cudaFree(p->d_parts);
   cudaFree(p->d_phik);
   cudaFree(p->d_sum);
+  cudaFree(p->d_done);
   delete p;
 }
 
@@ -287,10 +309,13 @@ eb_status eb_phik_plan_set_stream(eb_phik_plan* p, void* s)
 eb_status eb_phik_plan_set_algo(eb_phik_plan* p, int algo)
 {
   if (!p) return fail(EB_ERR_INVALID_ARGUMENT, "plan is NULL");
-  if (algo < 0 || algo > 3)
-    return fail(EB_ERR_INVALID_ARGUMENT, "algo must be 0 (auto), 1 (simple), 2 (dmma tiles) or 3 (dmma tiles, no mirror fold)");
-  if (algo >= 2 && !eb::phik_dmma_supported(p->nx, p->ny))
-    return fail(EB_ERR_UNSUPPORTED, "the DMMA phi_k kernel needs nx % 4 == 0 and nx >= 128");
+  if (algo < 0 || algo > 5)
+    return fail(EB_ERR_INVALID_ARGUMENT, "algo must be 0 (auto), 1 (simple), 2 / 3 (register-streamed DMMA tiles, with / without "
+                                         "the mirror fold) or 4 / 5 (TMA-staged DMMA tiles, with / without the mirror fold)");
+  if ((algo == 2 || algo == 3) && !eb::phik_dmma_supported(p->nx, p->ny))
+    return fail(EB_ERR_UNSUPPORTED, "the register-streamed DMMA phi_k kernel needs nx % 4 == 0 and nx >= 128");
+  if (algo >= 4 && (!eb::phik_tma_supported(p->nx, p->ny) || !eb::phik_tma_encoder()))
+    return fail(EB_ERR_UNSUPPORTED, "the TMA phi_k kernel needs an even nx >= 64 and a driver with cuTensorMapEncodeTiled");
   p->algo = algo;
   return EB_OK;
 }
@@ -326,10 +351,24 @@ static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* ph
   EB_TRACE("eb_phik_execute");
   EB_CUDA(cudaSetDevice(p->device));
   int algo = p->algo;
-  if (algo == 0) algo = (eb::phik_dmma_supported(p->nx, p->ny) && (long long)p->nx * p->ny >= (1 << 18)) ? 2 : 1;
+  const bool big = (long long)p->nx * p->ny >= (1 << 18);
+  if (algo == 0)
+    algo = (big && eb::phik_tma_supported(p->nx, p->ny) && eb::phik_tma_encoder() && (reinterpret_cast<uintptr_t>(phi_dev) & 15) == 0) ? 4 :
+           (big && eb::phik_dmma_supported(p->nx, p->ny))                                                                        ? 2 :
+                                                                                                                                   1;
   int nparts = 1;
-  const bool fold = algo == 2 && p->fold;
-  if (algo >= 2)
+  const bool fold = (algo == 2 || algo == 4) && p->fold;
+  if (algo >= 4)
+  {
+    // one launch: the last CTA to finish does the final sum (no separate phik_finalize)
+    const eb::PhikTmaOut out{ p->d_done, p->nb, phik_dev, phi_sum_dev, raw_dev };
+    nparts = eb::phik_tma_launch(phi_dev, p->nx, p->ny, fold ? p->d_cxtf : p->d_cxt, p->d_cy, p->d_parts, p->max_parts, fold,
+                                 out, p->stream);
+    if (nparts < 0) return fail(EB_ERR_CUDA, std::string("phik_tma_launch: ") + cudaGetErrorString(cudaGetLastError()));
+    p->launches += 1;
+    return EB_OK;
+  }
+  else if (algo >= 2)
   {
     nparts = eb::phik_dmma_launch(phi_dev, p->nx, p->ny, fold ? p->d_cxpf : p->d_cxp, p->d_cy, p->d_parts, p->max_parts,
                                   fold, p->stream);
@@ -466,25 +505,32 @@ inline bool use_v2(int nb)
 template <int MODEL, int NB, bool V2>
 struct SolveLaunch
 {
-  static size_t smem(int rounds)
+  static constexpr int kWide = []() constexpr {
+    if constexpr (V2)
+      return eb::Solve2Cfg<NB>::kWideWarps;
+    else
+      return eb::SolveCfg<NB>::kWideWarps;
+  }();
+  static size_t smem(int N, int warps = eb::kSolveWarps)
   {
     if constexpr (V2)
-      return eb::solve_smem_bytes(eb::Solve2Cfg<NB>::kTabDoubles, eb::Solve2Cfg<NB>::kFields, rounds);
+      return eb::solve2_smem_bytes<NB>(N, warps);
     else
-      return eb::solve_smem_bytes(eb::SolveCfg<NB>::kTabDoubles, eb::SolveCfg<NB>::kFields, rounds);
+      return eb::solve_smem_bytes(eb::SolveCfg<NB>::kTabDoubles, eb::SolveCfg<NB>::kFields, (N + 31) / 32, warps);
   }
-  static cudaError_t launch(const eb::SolveParams& p, int rounds, cudaStream_t s)
+  template <int WARPS>
+  static cudaError_t launch_w(const eb::SolveParams& p, cudaStream_t s)
   {
-    const size_t bytes = smem(rounds);
+    const size_t bytes = smem(p.N, WARPS);
     // the attribute is per device: remember what has been set, per instantiation and device
     static size_t configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     auto kernel = [] {
       if constexpr (V2)
-        return eb::solve_kernel2<MODEL, NB>;
+        return eb::solve_kernel2<MODEL, NB, WARPS>;
       else
-        return eb::solve_kernel<MODEL, NB>;
+        return eb::solve_kernel<MODEL, NB, WARPS>;
     }();
     if (bytes > configured[dev & 63])
     {
@@ -492,9 +538,37 @@ struct SolveLaunch
       if (e != cudaSuccess) return e;
       configured[dev & 63] = bytes;
     }
-    const int grid = (p.B + eb::kSolveWarps - 1) / eb::kSolveWarps;
-    kernel<<<grid, eb::kSolveWarps * 32, bytes, s>>>(p);
+    const int grid = (p.B + WARPS - 1) / WARPS;
+    kernel<<<grid, WARPS * 32, bytes, s>>>(p);
     return cudaGetLastError();
+  }
+  static cudaError_t launch(const eb::SolveParams& p, int rounds, cudaStream_t s)
+  {
+    (void)rounds;
+    // a batch that fits one wave of wide CTAs (one per SM) starts all of an SM's instances together
+    static const int sms = [] {
+      int dev = 0, n = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      return n;
+    }();
+    static const bool wide_ok = [] {
+      const char* e = std::getenv("EB_SOLVE_WIDE");
+      return !e || std::atoi(e) != 0;
+    }();
+    if (wide_ok && p.n_peer == 0 && p.B <= sms * kWide && p.B > sms * eb::kSolveWarps && smem(p.N, kWide) <= wide_limit())
+      return launch_w<kWide>(p, s);
+    return launch_w<eb::kSolveWarps>(p, s);
+  }
+  static size_t wide_limit()
+  {
+    static const size_t lim = [] {
+      int dev = 0, v = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      return (size_t)v;
+    }();
+    return lim;
   }
 };
 
@@ -518,21 +592,21 @@ cudaError_t launch_solve_m(const eb::SolveParams& p, int rounds, cudaStream_t s)
 }
 
 // dynamic shared memory of the solve kernel instantiation that serves `nb` (same dispatch as launch_solve_m)
-size_t solve_smem_for(int nb, int rounds)
+size_t solve_smem_for(int nb, int N)
 {
-  if (nb <= 8) return SolveLaunch<0, 8, false>::smem(rounds);
-  if (nb <= 10) return SolveLaunch<0, 10, false>::smem(rounds);
-  if (nb <= 12) return SolveLaunch<0, 12, false>::smem(rounds);
+  if (nb <= 8) return SolveLaunch<0, 8, false>::smem(N);
+  if (nb <= 10) return SolveLaunch<0, 10, false>::smem(N);
+  if (nb <= 12) return SolveLaunch<0, 12, false>::smem(N);
   if (use_v2(nb))
   {
-    if (nb <= 16) return SolveLaunch<0, 16, true>::smem(rounds);
-    if (nb <= 20) return SolveLaunch<0, 20, true>::smem(rounds);
-    return SolveLaunch<0, 24, true>::smem(rounds);
+    if (nb <= 16) return SolveLaunch<0, 16, true>::smem(N);
+    if (nb <= 20) return SolveLaunch<0, 20, true>::smem(N);
+    return SolveLaunch<0, 24, true>::smem(N);
   }
-  if (nb <= 16) return SolveLaunch<0, 16, false>::smem(rounds);
-  if (nb <= 20) return SolveLaunch<0, 20, false>::smem(rounds);
-  if (nb <= 24) return SolveLaunch<0, 24, false>::smem(rounds);
-  return SolveLaunch<0, 32, false>::smem(rounds);
+  if (nb <= 16) return SolveLaunch<0, 16, false>::smem(N);
+  if (nb <= 20) return SolveLaunch<0, 20, false>::smem(N);
+  if (nb <= 24) return SolveLaunch<0, 24, false>::smem(N);
+  return SolveLaunch<0, 32, false>::smem(N);
 }
 
 cudaError_t launch_solve(const eb::SolveParams& p, int model, int rounds, cudaStream_t s)
@@ -601,7 +675,7 @@ eb_status eb_create(const eb_config* cfg, eb_controller** out)
     // the fused kernel keeps per-step records of the whole horizon in shared memory: refuse horizons that cannot fit
     int optin = 0;
     EB_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
-    const size_t need = solve_smem_for(static_cast<int>(cfg->num_basis), (static_cast<int>(steps) + 31) / 32);
+    const size_t need = solve_smem_for(static_cast<int>(cfg->num_basis), static_cast<int>(steps));
     if (need > static_cast<size_t>(optin))
       return fail(EB_ERR_UNSUPPORTED, "eb_create: a horizon of " + std::to_string(steps) + " steps with num_basis " +
                                           std::to_string(cfg->num_basis) + " needs " + std::to_string(need) +
@@ -1451,6 +1525,11 @@ struct eb_grid
   double infl_thr = 0.0;
   int infl_pad = 0;
   int dilation_mode = 0;  // 0 auto (by pose count), 1 never, 2 always
+  // pipelined host path of DynamicWindow::control (dwa_host): second stream, and the dilation decision of the
+  // WHOLE batch while its chunks are launched one by one
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_side = nullptr;
+  long long batch_poses = -1;
 };
 
 namespace
@@ -1636,6 +1715,9 @@ void eb_grid_destroy(eb_grid* g)
   cudaFree(g->d_cost);
   cudaFree(g->d_ref);
   cudaFree(g->d_out);
+  if (g->side) cudaStreamDestroy(g->side);
+  if (g->ev_ready) cudaEventDestroy(g->ev_ready);
+  if (g->ev_side) cudaEventDestroy(g->ev_side);
   delete g;
 }
 
@@ -1784,7 +1866,8 @@ eb_status dwa_launch(eb_grid* g, eb::DwaParams& p)
   if (p.B == 0) return EB_OK;
   EB_CUDA(cudaSetDevice(g->device));
   {
-    const long long poses = (long long)p.B * p.col.steps * p.n[0] * p.n[1] * p.n[2];
+    const long long poses =
+        g->batch_poses >= 0 ? g->batch_poses : (long long)p.B * p.col.steps * p.n[0] * p.n[1] * p.n[2];
     const eb_status st = use_inflated(g, &p.col, poses * 4 >= (long long)g->view.xsize * g->view.ysize);
     if (st != EB_OK) return st;
   }
@@ -1869,19 +1952,92 @@ static eb_status dwa_host(eb_grid* g, const eb_collision* c, const eb_dwa* d, co
     EB_CUDA(cudaMalloc(&g->d_ref, sizeof(double) * ref_doubles));
     g->ref_cap = ref_doubles;
   }
-  cudaError_t e = cudaMemcpyAsync(g->d_a, x0, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_b, vb, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, g->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_ref, ref, sizeof(double) * ref_doubles, cudaMemcpyHostToDevice, g->stream);
-  if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e));
-  st = traj ? eb_dwa_control_traj_dev(g, c, d, g->d_a, g->d_b, g->d_ref, ncols, per_instance, dt_ref, count, g->d_out,
-                                      g->d_u, g->d_cost) :
-              eb_dwa_control_twist_dev(g, c, d, g->d_a, g->d_b, g->d_ref, count, g->d_out, g->d_u, g->d_cost);
+  auto pinned = [](const void* ptr) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+  };
+  auto run = [&](int lo, int n, bool copy_shared_ref) -> eb_status {
+    // one slice [lo, lo + n) of the batch on the grid's CURRENT stream: H2D, kernel, D2H
+    cudaStream_t s = g->stream;
+    const size_t o3 = 3 * (size_t)lo;
+    cudaError_t e = cudaMemcpyAsync(g->d_a + o3, x0 + o3, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_b + o3, vb + o3, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+    const double* dref = g->d_ref;
+    if (!traj || per_instance)
+    {
+      const size_t per = traj ? 3 * (size_t)ncols : 3;  // doubles of reference data per instance
+      dref = g->d_ref + per * (size_t)lo;
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(g->d_ref + per * (size_t)lo, ref + per * (size_t)lo, sizeof(double) * per * (size_t)n, cudaMemcpyHostToDevice, s);
+    }
+    else if (copy_shared_ref && e == cudaSuccess)
+      e = cudaMemcpyAsync(g->d_ref, ref, sizeof(double) * ref_doubles, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e));
+    eb_status r = traj ? eb_dwa_control_traj_dev(g, c, d, g->d_a + o3, g->d_b + o3, dref, ncols, per_instance, dt_ref, n,
+                                                 g->d_out + lo, g->d_u + o3, g->d_cost + lo) :
+                         eb_dwa_control_twist_dev(g, c, d, g->d_a + o3, g->d_b + o3, dref, n, g->d_out + lo, g->d_u + o3,
+                                                  g->d_cost + lo);
+    if (r != EB_OK) return r;
+    e = cudaMemcpyAsync(found + lo, g->d_out + lo, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(u_opt + o3, g->d_u + o3, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && min_cost)
+      e = cudaMemcpyAsync(min_cost + lo, g->d_cost + lo, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e));
+    return EB_OK;
+  };
+  // Large batches from page-locked caller buffers are cut into slices that alternate between two streams, so the
+  // copies of one slice overlap the kernel of the other (the copy engines and the SMs work at the same time);
+  // pageable buffers would serialise in the driver's staging path anyway.
+  constexpr int kSlice = 32768;
+  const bool pipelined = count >= 4 * kSlice && pinned(x0) && pinned(vb) && pinned(ref) && pinned(found) && pinned(u_opt) &&
+                         (!min_cost || pinned(min_cost));
+  if (!pipelined)
+  {
+    st = run(0, count, true);
+    if (st != EB_OK) return st;
+    cudaError_t e = cudaStreamSynchronize(g->stream);
+    if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e));
+    return EB_OK;
+  }
+  if (!g->side)
+  {
+    EB_CUDA(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking));
+    EB_CUDA(cudaEventCreateWithFlags(&g->ev_ready, cudaEventDisableTiming));
+    EB_CUDA(cudaEventCreateWithFlags(&g->ev_side, cudaEventDisableTiming));
+  }
+  cudaStream_t const main_stream = g->stream;
+  {
+    // the dilation decision belongs to the whole batch; what the first slice builds (on the main stream) the others reuse
+    const unsigned int ns[3] = { d->vx_samples ? d->vx_samples : 1u, d->vy_samples ? d->vy_samples : 1u,
+                                 d->vth_samples ? d->vth_samples : 1u };
+    const long long steps = (long long)static_cast<unsigned int>(std::abs(d->horizon / d->dt));
+    g->batch_poses = (long long)count * steps * ns[0] * ns[1] * ns[2];
+  }
+  st = EB_OK;
+  int slice = 0;
+  for (int lo = 0; lo < count && st == EB_OK; lo += kSlice, slice++)
+  {
+    const int n = std::min(kSlice, count - lo);
+    g->stream = (slice & 1) ? g->side : main_stream;
+    st = run(lo, n, slice == 0);
+    if (slice == 0 && st == EB_OK)
+    {
+      // map (possibly rebuilt) and shared reference data are in place once the first slice's work is enqueued
+      cudaEventRecord(g->ev_ready, main_stream);
+      cudaStreamWaitEvent(g->side, g->ev_ready, 0);
+    }
+  }
+  g->stream = main_stream;
+  g->batch_poses = -1;
+  cudaEventRecord(g->ev_side, g->side);
+  cudaStreamWaitEvent(main_stream, g->ev_side, 0);
+  cudaError_t e = cudaStreamSynchronize(main_stream);
   if (st != EB_OK) return st;
-  e = cudaMemcpyAsync(found, g->d_out, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(u_opt, g->d_u, sizeof(double) * 3 * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
-  if (e == cudaSuccess && min_cost)
-    e = cudaMemcpyAsync(min_cost, g->d_cost, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, g->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
   if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_dwa_control_host: ") + cudaGetErrorString(e));
   return EB_OK;
 }

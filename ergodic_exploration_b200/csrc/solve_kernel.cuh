@@ -357,16 +357,19 @@ struct SolveCfg
   static constexpr int kBlock = NB <= 12 ? NB : (NB == 20 ? EB_KB_20 : NB == 16 ? EB_KB_16 : 8);
   static constexpr int kMinBlocks =
       (NB <= 10 ? EB_MINB_10 : NB <= 12 ? 6 : NB <= 16 ? EB_MINB_16 : NB <= 24 ? EB_MINB_20 : 4) * 4 / kSolveWarps;
+  // Single-wave batches (configs[1]: 4096 instances on 148 SMs) run ONE CTA per SM with this many warps: the SM's
+  // instances then start together instead of behind 7 serial CTA launches (measured 34.9 -> 31.2 us at 4096 x nb 10)
+  static constexpr int kWideWarps = NB <= 10 ? 28 : NB <= 16 ? 24 : 16;
   static_assert(NB % kBlock == 0, "kx blocks must tile NB");
 };
 
-inline size_t solve_smem_bytes(int tab_doubles, int fields, int rounds)
+inline size_t solve_smem_bytes(int tab_doubles, int fields, int rounds, int warps = kSolveWarps)
 {
-  return sizeof(double) * kSolveWarps * (size_t)(tab_doubles + fields * 32 * rounds);
+  return sizeof(double) * warps * (size_t)(tab_doubles + fields * 32 * rounds);
 }
 
-template <int MODEL, int NB>
-__global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) solve_kernel(const SolveParams p)
+template <int MODEL, int NB, int WARPS = kSolveWarps>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB>::kMinBlocks : 1) solve_kernel(const SolveParams p)
 {
   using Cfg = SolveCfg<NB>;
   constexpr int TILES = (NB + 7) / 8;
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, SolveCfg<NB>::kMinBlocks) so
   const int npad = rounds * 32;
   const int nb = p.nb, K = nb * nb;
 
-  const int inst = blockIdx.x * kSolveWarps + warp;
+  const int inst = blockIdx.x * WARPS + warp;
   if (inst >= p.B) return;
   EB_PHASE(0);
 

@@ -53,7 +53,13 @@ struct Solve2Cfg
   static constexpr int kTabDoubles = kUnion + kStage;
   static constexpr int kFields = 8;                        // heading cos, sin; Fourier-frame x, y; cos, sin of a x; of b y
   static constexpr int kMinBlocks = (NB <= 16 ? EB_MINB2_16 : EB_MINB2_20) * 4 / kSolveWarps;
+  static constexpr int kWideWarps = NB <= 16 ? 24 : 16;  // one CTA per SM for single-wave batches (see SolveCfg)
 };
+
+// per-step records are kept for the horizon rounded up to a half-round (16 steps)
+__host__ __device__ inline int solve2_npad(int N) { return (N + 15) & ~15; }
+template <int NB>
+inline size_t solve2_smem_bytes(int N, int warps = kSolveWarps);
 
 // One half-round (16 states) of the rank-T update of the c_k accumulators.  lane = (axis = lane / 16, slot = lane % 16)
 // holds c1 = cos(pi * coordinate / l) of ITS axis of state `slot`; it runs the even / odd Chebyshev chains up to
@@ -120,8 +126,14 @@ __device__ __forceinline__ void coeff_half(double* __restrict__ tab, const int l
   }
 }
 
-template <int MODEL, int NB>
-__global__ void __launch_bounds__(kSolveWarps * 32, Solve2Cfg<NB>::kMinBlocks) solve_kernel2(const SolveParams p)
+template <int NB>
+inline size_t solve2_smem_bytes(int N, int warps)
+{
+  return sizeof(double) * warps * (size_t)(Solve2Cfg<NB>::kTabDoubles + Solve2Cfg<NB>::kFields * solve2_npad(N));
+}
+
+template <int MODEL, int NB, int WARPS = kSolveWarps>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? Solve2Cfg<NB>::kMinBlocks : 1) solve_kernel2(const SolveParams p)
 {
   using Cfg = Solve2Cfg<NB>;
   constexpr int TILES = Cfg::kTiles;
@@ -130,11 +142,11 @@ __global__ void __launch_bounds__(kSolveWarps * 32, Solve2Cfg<NB>::kMinBlocks) s
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rounds = (p.N + 31) >> 5;
-  const int npad = rounds * 32;
+  const int npad = solve2_npad(p.N);
   const int nb = p.nb, K = nb * nb;
   const int g = lane >> 2, q = lane & 3;
 
-  const int inst = blockIdx.x * kSolveWarps + warp;
+  const int inst = blockIdx.x * WARPS + warp;
   if (inst >= p.B) return;
 
   double* const tab = smem + warp * (Cfg::kTabDoubles + Cfg::kFields * npad);
@@ -214,10 +226,13 @@ __global__ void __launch_bounds__(kSolveWarps * 32, Solve2Cfg<NB>::kMinBlocks) s
     if (MODEL == kModelSimpleCart && !(fabs(u1 - 0.0) < 1.0e-12)) atomicOr(p.fault, 1);  // cart.hpp:167-170
     double xo, yo, tho, ce, se;
     rollout_round<MODEL>(p.dt, valid, lane, u0, u1, u2, cy, xo, yo, tho, ce, se);
-    rec[0 * npad + i] = ce;
-    rec[1 * npad + i] = se;
-    rec[2 * npad + i] = xo - p.xmin;
-    rec[3 * npad + i] = yo - p.ymin;
+    if (i < npad)
+    {
+      rec[0 * npad + i] = ce;
+      rec[1 * npad + i] = se;
+      rec[2 * npad + i] = xo - p.xmin;
+      rec[3 * npad + i] = yo - p.ymin;
+    }
     __syncwarp();
     const int nvalid = min(32, p.N - r * 32);
 #pragma unroll
@@ -290,19 +305,19 @@ __global__ void __launch_bounds__(kSolveWarps * 32, Solve2Cfg<NB>::kMinBlocks) s
   }
   __syncwarp();
 
-  // S as A fragments, folded with a_kx (R1) and b_ky (R2) once per instance
-  double SA[TILES][GKS], SB[TILES][GKS];
+  // S as A fragments, ONE copy for both bilinear forms: R1 = S (a_kx SX) and R2 = S CX share the A operand when the
+  // order weight a_kx rides on the sin chain (B operand) and b_ky is applied to R2's rows in the epilogue
+  double SF[TILES][GKS];
 #pragma unroll
   for (int mi = 0; mi < TILES; mi++)
 #pragma unroll
     for (int ks = 0; ks < GKS; ks++)
     {
       const int ky = 8 * mi + g, kx = 4 * ks + q;
-      const double sv = (ky < NB && kx < NB) ? Ssm[ky * Cfg::kSPitch + kx] : 0.0;
-      SA[mi][ks] = sv * ((double)kx * p.ax);
-      SB[mi][ks] = sv * ((double)ky * p.by);
+      SF[mi][ks] = (ky < NB && kx < NB) ? Ssm[ky * Cfg::kSPitch + kx] : 0.0;
     }
   __syncwarp();  // S has been read: the table region is free for the y tables
+  const double a4 = 4.0 * p.ax;  // a_kx advances by 4 a per k-step (kx = 4 ks + q)
 
   // ---- per round, last round first: metric gradient in 8-step tiles (:419-436), then the backward co-state
   //      pass and the control update of the same 32 steps (:277, :439-451) ----------------------------------
@@ -365,14 +380,17 @@ __global__ void __launch_bounds__(kSolveWarps * 32, Solve2Cfg<NB>::kMinBlocks) s
       double R1[TILES][2], R2[TILES][2];
 #pragma unroll
       for (int mi = 0; mi < TILES; mi++) R1[mi][0] = R1[mi][1] = R2[mi][0] = R2[mi][1] = 0.0;
+      double akx = (double)q * p.ax;
 #pragma unroll
       for (int ks = 0; ks < GKS; ks++)
       {
+        const double za = akx * Z;  // a_kx sin(kx a x_t)
+        akx += a4;
 #pragma unroll
         for (int mi = 0; mi < TILES; mi++)
         {
-          dmma_gr(R1[mi][0], R1[mi][1], SA[mi][ks], Z);
-          dmma_gr(R2[mi][0], R2[mi][1], SB[mi][ks], X);
+          dmma_gr(R1[mi][0], R1[mi][1], SF[mi][ks], za);
+          dmma_gr(R2[mi][0], R2[mi][1], SF[mi][ks], X);
         }
         if (ks + 1 < GKS)
         {
@@ -394,10 +412,11 @@ __global__ void __launch_bounds__(kSolveWarps * 32, Solve2Cfg<NB>::kMinBlocks) s
         {
           const double2 cy2 = *reinterpret_cast<const double2*>(tyc + ky * 8 + 2 * q);
           const double2 sy2 = *reinterpret_cast<const double2*>(tys + ky * 8 + 2 * q);
+          const double bky = (double)ky * p.by;
           v0 = fma(cy2.x, R1[mi][0], v0);
           v1 = fma(cy2.y, R1[mi][1], v1);
-          w0 = fma(sy2.x, R2[mi][0], w0);
-          w1 = fma(sy2.y, R2[mi][1], w1);
+          w0 = fma(sy2.x, bky * R2[mi][0], w0);
+          w1 = fma(sy2.y, bky * R2[mi][1], w1);
         }
       }
       // sum over the 8 row lanes g (lane = 4 g + q) by recursive halving:
@@ -427,8 +446,9 @@ __global__ void __launch_bounds__(kSolveWarps * 32, Solve2Cfg<NB>::kMinBlocks) s
     ex = -ex * p.w;
     ey = -ey * p.w;
 
-    const double ce = rec[0 * npad + i], se = rec[1 * npad + i];
-    const double xf = rec[2 * npad + i], yf = rec[3 * npad + i];
+    const int ir = min(i, npad - 1);  // lanes past the records are not valid steps
+    const double ce = rec[0 * npad + ir], se = rec[1 * npad + ir];
+    const double xf = rec[2 * npad + ir], yf = rec[3 * npad + ir];
     double u0 = 0.0, u1 = 0.0;
     if (i + 1 < p.N)
     {

@@ -51,7 +51,9 @@ typedef enum eb_status {
 /* models the controller can run (3-twist models only) */
 typedef enum eb_model {
   EB_MODEL_SIMPLE_CART = 0, /* models/cart.hpp:152-206 */
-  EB_MODEL_OMNI = 1         /* models/omni.hpp:164-215 */
+  EB_MODEL_OMNI = 1,        /* models/omni.hpp:164-215 */
+  EB_MODEL_CART = 2,        /* models/cart.hpp:60-145  -- forward rollout / model evaluation only (eb_rk4_solve_*) */
+  EB_MODEL_MECANUM = 3      /* models/omni.hpp:59-157  -- forward rollout / model evaluation only */
 } eb_model;
 
 /* Constructor arguments of ErgodicControl (ergodic_control.hpp:90-94) plus

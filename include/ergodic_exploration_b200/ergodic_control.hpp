@@ -240,7 +240,73 @@ struct model_id<models::Omni>
 {
   static constexpr int value = EB_MODEL_OMNI;
 };
+// model id + parameter block of the forward integrator (all four models)
+template <class ModelT>
+struct rk_model;
+template <>
+struct rk_model<models::SimpleCart>
+{
+  static constexpr int id = EB_MODEL_SIMPLE_CART;
+  static void params(const models::SimpleCart&, double*) {}
+};
+template <>
+struct rk_model<models::Omni>
+{
+  static constexpr int id = EB_MODEL_OMNI;
+  static void params(const models::Omni&, double*) {}
+};
+template <>
+struct rk_model<models::Cart>
+{
+  static constexpr int id = EB_MODEL_CART;
+  static void params(const models::Cart& m, double* p)
+  {
+    p[0] = m.wheel_radius;
+    p[1] = m.wheel_base;
+  }
+};
+template <>
+struct rk_model<models::Mecanum>
+{
+  static constexpr int id = EB_MODEL_MECANUM;
+  static void params(const models::Mecanum& m, double* p)
+  {
+    p[0] = m.wheel_radius;
+    p[1] = m.wheel_base_x;
+    p[2] = m.wheel_base_y;
+  }
+};
 }  // namespace b200
+
+// ---------------------------------------------------------------------------
+// RungeKutta, forward problem (integrator.hpp:60-152, 176-184)
+// ---------------------------------------------------------------------------
+/** @brief 4th order Runge-Kutta forward integration of a kinematic model on the GPU (rk4_solve_kernel).
+ *  The co-state overload of the reference (integrator.hpp:154-174) lives inside the fused control() kernel. */
+class RungeKutta
+{
+public:
+  explicit RungeKutta(double dt) : dt_(dt) {}
+
+  /** @brief Simulate the dynamics forward in time (integrator.hpp:135-152): xt is 3 x steps, headings wrapped */
+  template <class ModelT>
+  mat solve(const ModelT& model, const vec& x0, const mat& ut, double horizon) const
+  {
+    const auto steps = static_cast<unsigned int>(std::abs(horizon / dt_));
+    if (x0.n_elem != 3 || ut.n_cols < steps || ut.n_rows != static_cast<arma::uword>(eb_model_controls(b200::rk_model<ModelT>::id)))
+      throw std::logic_error("RungeKutta::solve: x0 must have 3 rows and ut one column of wheel / twist controls per step");
+    double par[3] = { 0.0, 0.0, 0.0 };
+    b200::rk_model<ModelT>::params(model, par);
+    mat xt(3, steps);
+    const eb_status st = eb_rk4_solve_host(0, b200::rk_model<ModelT>::id, par, dt_, horizon, x0.memptr(), ut.memptr(), 0, 1, xt.memptr());
+    if (st == EB_ERR_INVALID_ARGUMENT) throw std::invalid_argument(eb_last_error());  // cart.hpp:167-170
+    if (st != EB_OK) throw std::runtime_error(eb_last_error());
+    return xt;
+  }
+
+private:
+  double dt_;
+};
 
 // ---------------------------------------------------------------------------
 // Basis (basis.hpp:50-106)

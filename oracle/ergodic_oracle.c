@@ -676,6 +676,42 @@ void eo_phik_from_grid(const double *phi, int nx, int ny, double resolution, dou
   free(fk);
 }
 
+/* Row block [row_begin, row_begin + nrows) of eo_phik_from_grid for grids too large for one thread (C3: 8192^2 cells):
+ * the SAME per-cell arithmetic -- F_k = cos(kx (PI / lx) x) cos(ky (PI / ly) y) with the accumulated coordinates,
+ * acc_k += F_k * (phi / total) -- but the two cosine factors are tabulated per column / per row instead of being
+ * re-evaluated in every cell: the same inputs give the same doubles, only 2K libm calls per cell are saved.  `total`
+ * is sum(phi) over the WHOLE grid (target.cpp:87).  Partial sums of different row blocks are added by the caller. */
+void eo_phik_rows(const double *phi_rows, int nx, int row_begin, int nrows, double resolution, double lx, double ly,
+                  int nb, double total, double *acc /* nb*nb, overwritten */)
+{
+  const int K = nb * nb;
+  double *cxt = (double *)malloc(sizeof(double) * (size_t)nx * nb);
+  double *cyr = (double *)malloc(sizeof(double) * (size_t)nb);
+  double *fk = (double *)malloc(sizeof(double) * (size_t)K);
+  for (int k = 0; k < K; k++) acc[k] = 0.0;
+  double x = 0.0;
+  for (int j = 0; j < nx; j++) {
+    for (int kx = 0; kx < nb; kx++) cxt[(size_t)j * nb + kx] = cos(((double)kx * (EO_PI / lx)) * x); /* basis.cpp:85 */
+    x += resolution;
+  }
+  double y = 0.0;
+  for (int i = 0; i < row_begin; i++) y += resolution; /* the accumulated y of configTarget (:394-407) */
+  for (int i = 0; i < nrows; i++) {
+    for (int ky = 0; ky < nb; ky++) cyr[ky] = cos(((double)ky * (EO_PI / ly)) * y);
+    for (int j = 0; j < nx; j++) {
+      const double v = phi_rows[(size_t)i * nx + j] / total;
+      const double *cxj = cxt + (size_t)j * nb;
+      for (int ky = 0; ky < nb; ky++)
+        for (int kx = 0; kx < nb; kx++) fk[ky * nb + kx] = cxj[kx] * cyr[ky];
+      for (int k = 0; k < K; k++) acc[k] += fk[k] * v;
+    }
+    y += resolution;
+  }
+  free(cxt);
+  free(cyr);
+  free(fk);
+}
+
 /* ------------------------------------------------------------------------ */
 /* ErgodicControl                                                           */
 /* ------------------------------------------------------------------------ */

@@ -110,6 +110,8 @@ void eo_target_grid(double resolution, int nx, int ny, double *phi_grid /*2 x nx
  * temporary.  Used for config C3 where the literal code cannot run. */
 void eo_phik_from_grid(const double *phi, int nx, int ny, double resolution, double lx,
                        double ly, int nb, double *phik, double *phi_sum);
+void eo_phik_rows(const double *phi_rows, int nx, int row_begin, int nrows, double resolution, double lx, double ly,
+                  int nb, double total, double *acc);
 
 /* ---- ErgodicControl (ergodic_control.hpp) ------------------------------ */
 /* ---- occupancy-grid collision checking ------------- */

@@ -99,6 +99,14 @@ class _Controller:
             self._f("get_phik")(self._h, ph.ctypes.data_as(_dp))
         return ph
 
+    def set_phik(self, phik, lx, ly):
+        """phik_ and the basis extent set directly (restatement only): the configTarget of a control() whose map
+        extent equals (lx, ly) keeps them (ergodic_control.hpp:374-377)"""
+        assert not self._is_ref
+        ph, pp = _d(phik)
+        assert ph.size == self.K
+        self._f("set_phik")(self._h, pp, C.c_double(lx), C.c_double(ly))
+
     def opt_traj(self):
         xt = np.zeros((self.steps, 3))
         n = self._f("opt_traj")(self._h, xt.ctypes.data_as(_dp))
@@ -262,6 +270,41 @@ class Oracle:
         steps = int(abs(horizon / dt)); xt = np.zeros((steps, 3))
         cls.lib().eo_rk4_forward_cart(r, b, dt, horizon, p0, pu, xt.ctypes.data_as(_dp))
         return xt
+
+    @classmethod
+    def rk4_forward_mecanum(cls, r, bx, by, dt, horizon, x0, ut):
+        x0, p0 = _d(x0); ut, pu = _d(ut)
+        steps = int(abs(horizon / dt)); xt = np.zeros((steps, 3))
+        f = cls.lib().eo_rk4_forward_mecanum
+        f.argtypes = [C.c_double] * 5 + [_dp, _dp, _dp]
+        f(r, bx, by, dt, horizon, p0, pu, xt.ctypes.data_as(_dp))
+        return xt
+
+    @classmethod
+    def entropy(cls, p):
+        f = cls.lib().eo_entropy
+        f.restype, f.argtypes = C.c_double, [C.c_double]
+        return f(float(p))
+
+    @classmethod
+    def entropy_grid(cls, cells):
+        """entropy(int8 / 100) of every cell (numerics.hpp:164-179 over grid.cpp:177-184)"""
+        cells = np.ascontiguousarray(cells, dtype=np.int8)
+        out = np.zeros(cells.shape)
+        f = cls.lib().eo_entropy_grid
+        f.argtypes = [C.c_void_p, C.c_longlong, _dp]
+        f(cells.ctypes.data, cells.size, out.ctypes.data_as(_dp))
+        return out
+
+    @classmethod
+    def phik_rows(cls, phi_rows, row_begin, res, lx, ly, nb, total):
+        """un-normalised-by-rows partial of phik_from_grid: sum over the given rows of F_k * (phi / total)"""
+        phi_rows, pp = _d(phi_rows); nrows, nx = phi_rows.shape
+        acc = np.zeros(nb * nb)
+        f = cls.lib().eo_phik_rows
+        f.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, _dp]
+        f(pp, nx, int(row_begin), nrows, res, lx, ly, nb, float(total), acc.ctypes.data_as(_dp))
+        return acc
 
     @classmethod
     def basis_tables(cls, nb):
@@ -508,6 +551,32 @@ class RefLib:
         steps = int(abs(horizon / dt)); xt = np.zeros((steps, 3))
         cls.lib().ref_rk4_forward_cart(r, b, dt, horizon, p0, pu, xt.ctypes.data_as(_dp))
         return xt
+
+    @classmethod
+    def rk4_forward_mecanum(cls, r, bx, by, dt, horizon, x0, ut):
+        x0, p0 = _d(x0); ut, pu = _d(ut)
+        steps = int(abs(horizon / dt)); xt = np.zeros((steps, 3))
+        f = cls.lib().ref_rk4_forward_mecanum
+        f.argtypes = [C.c_double] * 5 + [_dp, _dp, _dp]
+        f(r, bx, by, dt, horizon, p0, pu, xt.ctypes.data_as(_dp))
+        return xt
+
+    @classmethod
+    def entropy(cls, p):
+        f = cls.lib().ref_entropy
+        f.restype, f.argtypes = C.c_double, [C.c_double]
+        return f(float(p))
+
+    @classmethod
+    def entropy_grid(cls, cells, res=0.05):
+        """entropy(GridMap::getCell(i)) for every cell, through the compiled reference"""
+        cells = np.ascontiguousarray(cells, dtype=np.int8)
+        ysize, xsize = cells.shape
+        out = np.zeros(cells.shape)
+        f = cls.lib().ref_entropy_grid
+        f.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_double, _dp]
+        f(cells.ctypes.data, xsize, ysize, float(res), out.ctypes.data_as(_dp))
+        return out
 
     @classmethod
     def basis_tables(cls, nb):

@@ -179,6 +179,21 @@ static int run_gpu(const ModelT& model, const mat& Rinv, const vec& umin, const 
     x(1) += 0.1 * u(1);
     x(2) = normalize_angle_PI(x(2) + 0.1 * u(2));
   }
+  {
+    // the reference's integrator test (test/test_integrator.cpp:44-73) through the GPU RungeKutta adapter,
+    // and a Mecanum rollout for the Python side to compare with the oracle
+    const models::Cart cart(0.1, 2.0);
+    const mat ut(2, 4, arma::fill::ones);
+    const RungeKutta rk4(0.1);
+    const mat xt = rk4.solve(cart, vec({ 0.0, 0.0, 0.0 }), ut, 0.4);
+    print_vec("rkcart", xt.memptr(), xt.n_elem);
+    const models::Mecanum mec(0.05, 0.3, 0.2);
+    mat um(4, 6);
+    for (unsigned c = 0; c < 6; c++)
+      for (unsigned r = 0; r < 4; r++) um(r, c) = 3.0 * std::sin(1.0 + r + 2.0 * c);
+    const mat xm = RungeKutta(0.05).solve(mec, vec({ 0.4, -0.2, 1.1 }), um, 0.31);
+    print_vec("rkmec", xm.memptr(), xm.n_elem);
+  }
   // value semantics: a copy is deep (exploration.hpp:137-138)
   ErgodicControl twin = ec;
   const vec ua = ec.control(grid, x), ub = twin.control(grid, x);

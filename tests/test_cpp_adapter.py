@@ -76,6 +76,13 @@ def test_adapter_closed_loop_matches_oracle(demo, model):
     vals = Oracle.target_fill([[2.5, 2.5], [8.5, 2.5]], [[1.5, 1.5], [1.5, 1.5]], [0.0, 0.0], pts)
     assert_coeff_close(rec["fill"][0], vals, "Target::fill")
     assert_coeff_close(rec["sc"][0], Oracle.spatial_coeff(10.0, 10.0, 10, vals, pts), "spatialCoeff")
+    # RungeKutta adapter: test/test_integrator.cpp:44-73 on the GPU, and a Mecanum rollout against the oracle
+    rk = rec["rkcart"][0].reshape(4, 3)
+    for i in range(4):
+        assert abs(rk[i, 0] - 0.01 * (i + 1)) <= 4 * np.spacing(0.01 * (i + 1)) and rk[i, 1] == 0.0 and rk[i, 2] == 0.0
+    um = np.array([[3.0 * np.sin(1.0 + r + 2.0 * c) for r in range(4)] for c in range(6)])
+    want = Oracle.rk4_forward_mecanum(0.05, 0.3, 0.2, 0.05, 0.31, [0.4, -0.2, 1.1], um)
+    assert_abs_rel_close(rec["rkmec"][0].reshape(6, 3), want, "Mecanum RK4 through the adapter")
     # batched face
     xb = rec["xb"][0].reshape(3, 3)
     for i in range(3):

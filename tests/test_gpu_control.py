@@ -1,5 +1,7 @@
 """-m gpu: parity of the CUDA control() path (through the C ABI) against the
 CPU oracle on the same seeded inputs.  Tolerances: see tests/helpers.py."""
+import os
+
 import numpy as np
 import pytest
 
@@ -418,3 +420,85 @@ def test_keep_ck_switch():
     assert a.get_ck().shape == (B, 100)
     with pytest.raises(Exception):
         b.get_ck()
+
+
+def test_wide_cta_path_single_wave_batch():
+    """batches between 4 x #SM and kWideWarps x #SM instances run one wide CTA per SM (28 warps at nb = 10,
+    24 at nb = 16, 16 at nb = 20): same numbers as the oracle on sampled instances, and bit-identical to the
+    4-warp launch of the same kernel (EB_SOLVE_WIDE only changes the launch shape)"""
+    import subprocess
+    import sys
+
+    for model, nb, horizon, B in ((MODEL_OMNI, 10, 5.0, 4096), (MODEL_OMNI, 16, 5.0, 3000), (MODEL_SIMPLE_CART, 20, 10.0, 2000)):
+        rng = np.random.default_rng(nb)
+        gpu = make_gpu(model, B, nb=nb, horizon=horizon)
+        x = random_states(rng, B)
+        ut = warm_ut(rng, B, gpu.steps, model)
+        gpu.set_ut(ut)
+        metric = np.empty(B)
+        u0 = gpu.control(BOUNDS_10, x, metric=metric)
+        ut_new = gpu.get_ut()
+        for i in rng.choice(B, 12, replace=False):
+            o = make_oracle(model, nb=nb, horizon=horizon)
+            o.set_ut(ut[i])
+            want = o.control(BOUNDS_10, x[i])
+            assert_abs_rel_close(u0[i], want, f"u0 nb={nb} inst {i}")
+            assert_abs_rel_close(ut_new[i], o.get_ut(), f"ut_ nb={nb} inst {i}")
+            assert_abs_rel_close(metric[i], o.last()["metric"], "metric")
+    # launch-shape invariance, in a fresh process with the wide launch switched off
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from helpers import *\nfrom oracle.pyoracle import MODEL_OMNI\n"
+            "rng = np.random.default_rng(10); gpu = make_gpu(MODEL_OMNI, 4096, nb=10)\n"
+            "x = random_states(rng, 4096); ut = warm_ut(rng, 4096, gpu.steps, MODEL_OMNI); gpu.set_ut(ut)\n"
+            "u0 = gpu.control(BOUNDS_10, x); np.save(sys.argv[1], u0)\n") % (os.path.dirname(os.path.abspath(__file__)),
+                                                                          os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import tempfile
+    outs = []
+    for wide in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            subprocess.check_call([sys.executable, "-c", code, f.name], env=dict(os.environ, EB_SOLVE_WIDE=wide))
+            outs.append(np.load(f.name))
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_replay_index_out_of_range_is_reported():
+    """buffer.cpp:84,103: memory_.at(i) throws std::out_of_range; here EB_ERR_OUT_OF_RANGE after the step"""
+    from ergodic_exploration_b200 import ErgodicB200Error, capi
+
+    rng = np.random.default_rng(3)
+    B, bs = 8, 4
+    gpu = make_gpu(MODEL_OMNI, B, batch_size=bs)
+    for _ in range(bs + 3):
+        gpu.addStateMemory(random_states(rng, B))
+    x = random_states(rng, B)
+    idx = rng.integers(0, bs + 3, size=(B, bs)).astype(np.int32)
+    gpu.control(BOUNDS_10, x, mem_idx=idx)  # fine
+    idx[2, 1] = bs + 3  # one past the stored states
+    with pytest.raises(ErgodicB200Error) as e:
+        gpu.control(BOUNDS_10, x, mem_idx=idx)
+    assert e.value.status == capi.EB_ERR_OUT_OF_RANGE
+    idx[2, 1] = -1
+    with pytest.raises(ErgodicB200Error):
+        gpu.control(BOUNDS_10, x, mem_idx=idx)
+    idx[2, 1] = 0
+    gpu.control(BOUNDS_10, x, mem_idx=idx)  # the controller stays usable
+
+
+def test_horizon_too_long_for_shared_memory_is_refused_at_construction():
+    from ergodic_exploration_b200 import ErgodicB200Error, capi
+
+    with pytest.raises(ErgodicB200Error) as e:
+        make_gpu(MODEL_OMNI, 4, nb=10, horizon=200.0)  # 2000 steps x 8 fields x 4 warps > 227 KB
+    assert e.value.status == capi.EB_ERR_UNSUPPORTED
+    make_gpu(MODEL_OMNI, 4, nb=10, horizon=60.0).close()  # 600 steps still fit
+
+
+def test_nan_guard_reports_non_finite_controls():
+    rng = np.random.default_rng(4)
+    from ergodic_exploration_b200 import ErgodicB200Error
+
+    gpu = make_gpu(MODEL_OMNI, 4)
+    x = random_states(rng, 4)
+    x[1, 0] = np.nan
+    with pytest.raises(ErgodicB200Error):
+        gpu.control(BOUNDS_10, x)
