@@ -94,6 +94,7 @@ SIGNATURES = {
     "eb_config_target": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double, _ip]),
     "eb_set_phik": (C.c_int, [_vp, _vp, C.c_double, C.c_double]),
     "eb_get_phik": (C.c_int, [_vp, _vp, _dp, _dp]),
+    "eb_reserve_state_memory": (C.c_int, [_vp, C.c_longlong]),
     "eb_add_state_memory_host": (C.c_int, [_vp, _vp]),
     "eb_add_state_memory_dev": (C.c_int, [_vp, _vp]),
     "eb_control_host": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp, _vp]),
@@ -145,6 +146,7 @@ SIGNATURES = {
     "eb_peer_gathered_dev": (_vp, [_vp, C.c_ulonglong]),
     "eb_peer_group_steps": (C.c_ulonglong, [_vp]),
     "eb_peer_group_fused": (C.c_int, [_vp, C.c_int]),
+    "eb_gather_fuse_min_batch": (C.c_int, []),
     "eb_phik_plan_create_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                          C.c_double, C.c_int, C.c_double, C.c_double, C.POINTER(_vp)]),
     "eb_map_target_create": (C.c_int, [C.c_int, C.c_uint, C.c_uint, C.c_double, C.c_int, C.POINTER(_vp)]),

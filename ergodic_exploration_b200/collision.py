@@ -167,9 +167,11 @@ class DynamicWindow:
     def steps(self) -> int:
         return int(abs(self.cfg.horizon / self.cfg.dt))
 
-    def control(self, grid: GridMap, x0, vb, vref=None, xt_ref=None, dt_ref: float = 0.0, min_cost=None):
+    def control(self, grid: GridMap, x0, vb, vref=None, xt_ref=None, dt_ref: float = 0.0, min_cost=None, out=None):
         """vref: (B, 3) reference twists, or xt_ref: a reference trajectory (ncols, 3) shared by the batch
-        or (B, ncols, 3) per instance (e.g. ErgodicControl.optTraj()) with its time step dt_ref"""
+        or (B, ncols, 3) per instance (e.g. ErgodicControl.optTraj()) with its time step dt_ref.
+        Host path: ``out=(found int32 (B,), u (B, 3))`` lets a control loop reuse (page-locked) result buffers;
+        with every buffer page-locked, large batches are copied and computed in overlapping slices."""
         if (vref is None) == (xt_ref is None):
             raise ValueError("give either vref or xt_ref")
         grid._stream()
@@ -194,7 +196,12 @@ class DynamicWindow:
         x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, 3)
         vb = np.ascontiguousarray(vb, dtype=np.float64).reshape(-1, 3)
         n = len(x0)
-        found, u = np.empty(n, dtype=np.int32), np.empty((n, 3))
+        if out is not None:
+            found, u = out
+            assert found.dtype == np.int32 and found.size == n and u.dtype == np.float64 and u.size == 3 * n
+            assert found.flags.c_contiguous and u.flags.c_contiguous
+        else:
+            found, u = np.empty(n, dtype=np.int32), np.empty((n, 3))
         mc = min_cost.ctypes.data if min_cost is not None else None
         if vref is not None:
             vref = np.ascontiguousarray(vref, dtype=np.float64).reshape(-1, 3)

@@ -279,6 +279,10 @@ class ErgodicControl:
         check(self._lib.eb_config_target(self._h, *b, C.byref(rebuilt)))
         return bool(rebuilt.value)
 
+    def reserve_memory(self, count: int) -> None:
+        """room for `count` stored states up front (no re-allocation inside the control loop)"""
+        check(self._lib.eb_reserve_state_memory(self._h, int(count)))
+
     def addStateMemory(self, x) -> None:
         if _is_cuda_tensor(x):
             self._sync_stream()

@@ -619,6 +619,14 @@ eb_status ensure_hist(eb_controller* c, long long need)
 {
   if (need <= c->hist_cap) return EB_OK;
   long long cap = std::max<long long>(c->hist_cap ? 2 * c->hist_cap : 128, need);
+  {
+    // a replay buffer whose full size is a small part of the device memory is allocated once: growing it later
+    // means cudaMalloc + copy + cudaFree in the middle of a control loop (and a re-mapping on every peer when the
+    // context has peer access enabled)
+    size_t free_b = 0, total_b = 0;
+    const size_t full = sizeof(double) * 3 * (size_t)c->B * (size_t)c->cfg.buffer_size;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && full <= free_b / 8) cap = std::max<long long>(cap, c->cfg.buffer_size);
+  }
   cap = std::min<long long>(cap, std::max<long long>((long long)c->cfg.buffer_size, need));
   double* nh = nullptr;
   EB_CUDA(cudaMalloc(&nh, sizeof(double) * 3 * (size_t)c->B * (size_t)cap));
@@ -940,6 +948,14 @@ static eb_status add_state_memory(eb_controller* c, const double* x, cudaMemcpyK
   if (kind == cudaMemcpyHostToDevice) EB_CUDA(cudaStreamSynchronize(c->stream));
   c->mem_count++;
   return EB_OK;
+}
+
+// room for `count` stored states up front (at most buffer_size): no re-allocation inside the control loop
+eb_status eb_reserve_state_memory(eb_controller* c, long long count)
+{
+  if (!c || count < 0) return fail(EB_ERR_INVALID_ARGUMENT, "eb_reserve_state_memory: bad argument");
+  EB_CUDA(cudaSetDevice(c->cfg.device));
+  return ensure_hist(c, std::min<long long>(count, (long long)c->cfg.buffer_size));
 }
 
 eb_status eb_add_state_memory_host(eb_controller* c, const double* x)
@@ -1273,6 +1289,17 @@ eb_status eb_target_fill_host(int device, int ng, const double* mu, const double
 // ---------------------------------------------------------------------------
 }  // extern "C"
 
+// Batches of at least this many instances publish their first twists from inside the solve kernel; smaller
+// (single-wave) batches from the group's side stream (peer_gather.cuh).  EB_GATHER_FUSE_MIN_BATCH overrides.
+extern "C" int eb_gather_fuse_min_batch(void)
+{
+  static const int v = [] {
+    const char* e = std::getenv("EB_GATHER_FUSE_MIN_BATCH");
+    return e ? std::atoi(e) : 8192;
+  }();
+  return v;
+}
+
 struct eb_peer_group
 {
   int device = 0, rank = 0, world = 1;
@@ -1289,7 +1316,7 @@ struct eb_peer_group
   cudaStream_t side = nullptr;
   cudaEvent_t solved[eb::kPeerBuffers] = {}, published[eb::kPeerBuffers] = {};
   unsigned int* side_counter = nullptr;
-  int fuse_min_batch = 32768;                   // batches at least this large publish from inside the solve kernel
+  int fuse_min_batch = eb_gather_fuse_min_batch();  // batches at least this large publish from inside the solve kernel
 };
 
 extern "C" {
@@ -1327,7 +1354,6 @@ eb_status eb_peer_group_create(int device, int rank, int world, long long elems_
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->solved[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->published[k], cudaEventDisableTiming);
   }
-  if (const char* env = std::getenv("EB_GATHER_FUSE_MIN_BATCH")) g->fuse_min_batch = std::atoi(env);
   if (e == cudaSuccess) e = cudaMemset(g->flags, 0, sizeof(unsigned long long) * eb::kMaxPeers);
   if (e == cudaSuccess) e = cudaMemset(g->counter, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -2166,7 +2192,7 @@ eb_status eb_map_target_execute_dev(eb_map_target* m, const signed char* cells_d
   const long long cells = (long long)m->xsize * m->ysize;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
-  const int grid = (int)std::min<long long>((cells / 16 + 255) / 256 + 1, (long long)sms * 8);
+  const int grid = (int)std::min<long long>((cells / 512 + 7) / 8 + 1, (long long)sms * 8);  // 8 warps per CTA, 512 cells per warp iteration
   eb::entropy_density_kernel<<<grid, 256, 0, m->stream>>>(cells_dev, cells, m->d_lut, m->d_phi);
   m->launches += 1;
   EB_CUDA(cudaGetLastError());

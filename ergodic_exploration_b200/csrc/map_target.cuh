@@ -33,29 +33,34 @@ __global__ void entropy_lut_kernel(double* __restrict__ lut)
   lut[b] = e;
 }
 
-// Phi = lut[cell]; 16 cells per thread (one 16-byte load, eight 16-byte stores), grid-stride
+// Phi = lut[cell].  A warp converts 512 consecutive cells per iteration: lane l takes the cell pairs l, l + 32, ..
+// (2-byte loads, 64 contiguous bytes per instruction) and writes them as double2 -- 512 contiguous bytes per store
+// instruction, every 128-byte line written by one instruction.  1 B read + 8 B written per cell: HBM-bound.
 __global__ void __launch_bounds__(256) entropy_density_kernel(const signed char* __restrict__ cells, long long n,
                                                               const double* __restrict__ lut_g, double* __restrict__ phi)
 {
   __shared__ double lut[256];
   lut[threadIdx.x] = lut_g[threadIdx.x];
   __syncthreads();
-  const long long n16 = n >> 4;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool aligned = (reinterpret_cast<uintptr_t>(cells) & 1) == 0 && (reinterpret_cast<uintptr_t>(phi) & 15) == 0;
+  const long long nblk = aligned ? (n >> 9) : 0;  // full 512-cell blocks
+  const unsigned short* c2 = reinterpret_cast<const unsigned short*>(cells);
+  double2* o2 = reinterpret_cast<double2*>(phi);
+  for (long long b = warp; b < nblk; b += nwarps)
   {
-    const uint4 w = __ldg(reinterpret_cast<const uint4*>(cells) + i);
-    const unsigned int ws[4] = { w.x, w.y, w.z, w.w };
-    double2* out = reinterpret_cast<double2*>(phi + (i << 4));
+    const long long p0 = (b << 8) + lane;  // pair index
+    unsigned short w[8];
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-    {
-      out[2 * k] = make_double2(lut[ws[k] & 255u], lut[(ws[k] >> 8) & 255u]);
-      out[2 * k + 1] = make_double2(lut[(ws[k] >> 16) & 255u], lut[ws[k] >> 24]);
-    }
+    for (int k = 0; k < 8; k++) w[k] = __ldg(c2 + p0 + 32 * k);
+#pragma unroll
+    for (int k = 0; k < 8; k++) o2[p0 + 32 * k] = make_double2(lut[w[k] & 255u], lut[w[k] >> 8]);
   }
-  // tail (n not a multiple of 16)
-  for (long long i = (n16 << 4) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  // tail (and unaligned buffers): one cell per thread
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (nblk << 9) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     phi[i] = lut[(unsigned char)cells[i]];
 }
 

@@ -79,6 +79,7 @@ __device__ double g_dbg[4096 * 16];  // debug build only: per-step intermediates
 // class of work from the fused kernel so that its marginal cost can be read off the kernel time.
 //  1: c_k DMMAs -> integer xor of the operands   2: gradient DMMAs -> xor   4: c_k table recurrences + stores
 //  8: sin/cos polynomials -> 2 flops            16: gradient table recurrences + stores   64: warp scans -> identity
+//  128: v1 kernel returns at once (launch + drain cost of the grid)
 #ifndef EB_ABL
 #define EB_ABL 0
 #endif
@@ -382,6 +383,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
 
   const int inst = blockIdx.x * WARPS + warp;
   if (inst >= p.B) return;
+#if EB_ABL & 128
+  if (lane < 3) p.u0[(size_t)inst * 3 + lane] = 0.0;  // ablation timing only: the launch itself
+  return;
+#endif
+#ifdef EB_STAGGER_NS
+  // experiment: de-phase the warps of a single-wave launch (every warp runs the same phases in lockstep otherwise)
+  if (WARPS > kSolveWarps) __nanosleep((unsigned)(EB_STAGGER_NS) * (unsigned)(warp % EB_STAGGER_GROUPS));
+#endif
   EB_PHASE(0);
 
   // per-warp shared memory: the two cosine tables, then the per-step records

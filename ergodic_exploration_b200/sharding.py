@@ -99,14 +99,10 @@ class ShardedErgodicControl:
         return all_gather_rows(u0, self.total, self.group)
 
 
-FUSE_MIN_BATCH_DEFAULT = 8192  # keep in step with eb_peer_group::fuse_min_batch (csrc/ergodic_b200.cu)
-
-
 def gather_mode_for_batch(batch: int) -> str:
     """which branch of eb_control_dev_gather publishes a batch of this size"""
-    import os
-    thr = int(os.environ.get("EB_GATHER_FUSE_MIN_BATCH", FUSE_MIN_BATCH_DEFAULT))
-    if batch >= thr:
+    lib = capi.load()
+    if lib.eb_gather_fuse_min_batch() <= batch:
         return ("fused into the solve kernel: every warp stores its row into all ranks' gathered buffers "
                 "(P2P stores over NVLink peer memory), arrival flags raised by the launch's last warp")
     return ("solve kernel writes u0 locally, peer_publish_kernel on the group's side stream copies the block to all "

@@ -119,6 +119,8 @@ eb_status eb_get_phik(const eb_controller *c, double *phik, double *lx, double *
 
 /* ---- replay memory (addStateMemory :345-348, buffer.cpp:54-62) ---------- */
 /* x: 3 x B.  Silently dropped when buffer_size states are stored. */
+/* room for `count` stored states up front (capped at buffer_size): keeps allocations out of the control loop */
+eb_status eb_reserve_state_memory(eb_controller *c, long long count);
 eb_status eb_add_state_memory_host(eb_controller *c, const double *x);
 eb_status eb_add_state_memory_dev(eb_controller *c, const double *x_dev);
 
@@ -248,6 +250,7 @@ double *eb_peer_gathered_dev(eb_peer_group *g, unsigned long long step);
 unsigned long long eb_peer_group_steps(const eb_peer_group *g);
 /* 1: a batch of this size publishes from inside the solve kernel, 0: from the group's side stream */
 int eb_peer_group_fused(const eb_peer_group *g, int batch);
+int eb_gather_fuse_min_batch(void); /* the threshold behind eb_peer_group_fused (EB_GATHER_FUSE_MIN_BATCH overrides) */
 /* NOTE (equal shards): every rank's row block starts at rank * elems_per_rank in every gathered buffer, so all
  * ranks of a group MUST be created with the same elems_per_rank (= 3 * batch); uneven shards have to be padded
  * by the caller (the Python PeerGather checks this with one all_reduce at construction). */

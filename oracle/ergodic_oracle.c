@@ -465,6 +465,22 @@ void eo_entropy_grid(const signed char *cells, long long n, double *out)
   for (long long i = 0; i < n; i++) out[i] = eo_entropy((double)cells[i] / 100.0);
 }
 
+/* test tooling (tools/edge_study.py): `steps` constant-twist steps of integrate_twist + normalize_angle_PI
+ * (numerics.hpp:273-298, 77-89, as validate_control / DynamicWindow chain them) for n poses; out: [steps][n][3] */
+void eo_integrate_twist_chain(const double *x0, const double *u, double dt, long long n, int steps, double *out)
+{
+  for (long long i = 0; i < n; i++) {
+    double x[3] = { x0[3 * i], x0[3 * i + 1], x0[3 * i + 2] };
+    for (int k = 0; k < steps; k++) {
+      double xn[3];
+      eo_integrate_twist(x, u + 3 * i, dt, xn);
+      xn[2] = eo_normalize_angle_pi(xn[2]);
+      memcpy(x, xn, sizeof(x));
+      memcpy(out + ((size_t)k * (size_t)n + (size_t)i) * 3, x, sizeof(x));
+    }
+  }
+}
+
 /* rhodot ergodic_control.hpp:65-69: -gdx - dbar - fdx.t()*rho */
 static void rhodot(const double rho[3], const double gdx[3], const double dbar[3],
                    const double A[9], double out[3])

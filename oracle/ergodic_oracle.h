@@ -73,6 +73,7 @@ int eo_rk4_forward_mecanum(double r, double bx, double by, double dt, double hor
                            const double x0[3], const double *ut /*4 x steps*/, double *xt);
 double eo_entropy(double p);                                       /* numerics.hpp:164-179 */
 void eo_entropy_grid(const signed char *cells, long long n, double *out); /* + grid.cpp:177-184 */
+void eo_integrate_twist_chain(const double *x0, const double *u, double dt, long long n, int steps, double *out);
 void eo_rk4_backward(int model, double dt, int steps, const double rhoT[3],
                      const double *xt, const double *ut, const double *edx,
                      const double *bdx, double *rhot);

@@ -67,6 +67,30 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.eb_create(C.byref(cfg), C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
     assert h.value is None
     assert lib.eb_control_host(None, 0, 1, 0, 1, None, None, None, None) == capi.EB_ERR_INVALID_ARGUMENT
+    # round-2 entry points
+    assert lib.eb_map_target_create(0, 0, 10, 0.05, 8, C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
+    assert lib.eb_map_target_create(0, 10, 10, 0.05, 33, C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
+    assert lib.eb_rk4_solve_host(0, 7, None, 0.1, 1.0, None, None, 0, 1, None) == capi.EB_ERR_INVALID_ARGUMENT
+    assert lib.eb_model_eval_host(0, 2, None, None, None, 1, None, None, None, None) == capi.EB_ERR_INVALID_ARGUMENT  # Cart needs params
+    assert [lib.eb_model_controls(m) for m in range(5)] == [3, 3, 2, 4, 0]
+    assert lib.eb_set_phik_dev(None, None, 1.0, 1.0) == capi.EB_ERR_INVALID_ARGUMENT
+    assert lib.eb_gather_fuse_min_batch() > 0
+
+
+def test_new_entry_points_have_no_cpu_fallback(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import ergodic_exploration_b200 as eb
+
+    with pytest.raises(eb.ErgodicB200Error) as e:
+        eb.MapTarget(64, 64, 0.05, 8)
+    assert e.value.status == eb.EB_ERR_NO_DEVICE
+    with pytest.raises(eb.ErgodicB200Error):
+        eb.RungeKutta(0.1).solve(eb.Cart(0.1, 2.0), [0.0, 0.0, 0.0], np.ones((4, 2)), 0.4)
+    with pytest.raises(eb.ErgodicB200Error):
+        eb.Omni()([0.0, 0.0, 0.0], [1.0, 0.0, 0.0])
 
 
 def test_no_cpu_fallback(lib):
