@@ -149,6 +149,12 @@ SIGNATURES = {
     "eb_gather_fuse_min_batch": (C.c_int, []),
     "eb_phik_plan_create_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                          C.c_double, C.c_int, C.c_double, C.c_double, C.POINTER(_vp)]),
+    "eb_phik_peer_blob_bytes": (C.c_int, []),
+    "eb_phik_peer_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "eb_phik_peer_export": (C.c_int, [_vp, _vp]),
+    "eb_phik_peer_connect": (C.c_int, [_vp, _vp]),
+    "eb_phik_peer_destroy": (None, [_vp]),
+    "eb_phik_execute_allreduce_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "eb_map_target_create": (C.c_int, [C.c_int, C.c_uint, C.c_uint, C.c_double, C.c_int, C.POINTER(_vp)]),
     "eb_map_target_destroy": (None, [_vp]),
     "eb_map_target_set_stream": (C.c_int, [_vp, _vp]),

@@ -110,6 +110,7 @@ struct eb_phik_plan
   double *d_parts = nullptr;                // partial 32x32 blocks
   double *d_phik = nullptr, *d_sum = nullptr;  // staging for the _host call
   unsigned int* d_done = nullptr;              // arrival counter of the TMA kernel's fused final sum
+  const eb::PhikTmaPeer* peer = nullptr;       // set for the duration of eb_phik_execute_allreduce_dev
   int max_parts = 0;
   long long launches = 0;
 };
@@ -361,7 +362,7 @@ static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* ph
   if (algo >= 4)
   {
     // one launch: the last CTA to finish does the final sum (no separate phik_finalize)
-    const eb::PhikTmaOut out{ p->d_done, p->nb, phik_dev, phi_sum_dev, raw_dev };
+    const eb::PhikTmaOut out{ p->d_done, p->nb, phik_dev, phi_sum_dev, raw_dev, p->peer };
     nparts = eb::phik_tma_launch(phi_dev, p->nx, p->ny, fold ? p->d_cxtf : p->d_cxt, p->d_cy, p->d_parts, p->max_parts, fold,
                                  out, p->stream);
     if (nparts < 0) return fail(EB_ERR_CUDA, std::string("phik_tma_launch: ") + cudaGetErrorString(cudaGetLastError()));
@@ -499,7 +500,11 @@ inline bool use_v2(int nb)
     const char* e = std::getenv("EB_SOLVE_V1");
     return e && std::atoi(e) != 0;
   }();
-  return !v1 && nb > 12 && nb <= 24;
+  static const bool small = [] {  // experiment: the v2 kernel for num_basis 9..12 as well
+    const char* e = std::getenv("EB_SOLVE_V2_SMALL");
+    return e && std::atoi(e) != 0;
+  }();
+  return !v1 && nb > (small ? 8 : 12) && nb <= 24;
 }
 
 template <int MODEL, int NB, bool V2>
@@ -577,6 +582,8 @@ cudaError_t launch_solve_m(const eb::SolveParams& p, int rounds, cudaStream_t s)
 {
   const int nb = p.nb;
   if (nb <= 8) return SolveLaunch<MODEL, 8, false>::launch(p, rounds, s);
+  if (nb <= 12 && use_v2(nb))
+    return nb <= 10 ? SolveLaunch<MODEL, 10, true>::launch(p, rounds, s) : SolveLaunch<MODEL, 12, true>::launch(p, rounds, s);
   if (nb <= 10) return SolveLaunch<MODEL, 10, false>::launch(p, rounds, s);
   if (nb <= 12) return SolveLaunch<MODEL, 12, false>::launch(p, rounds, s);
   if (use_v2(nb))
@@ -595,6 +602,7 @@ cudaError_t launch_solve_m(const eb::SolveParams& p, int rounds, cudaStream_t s)
 size_t solve_smem_for(int nb, int N)
 {
   if (nb <= 8) return SolveLaunch<0, 8, false>::smem(N);
+  if (nb <= 12 && use_v2(nb)) return nb <= 10 ? SolveLaunch<0, 10, true>::smem(N) : SolveLaunch<0, 12, true>::smem(N);
   if (nb <= 10) return SolveLaunch<0, 10, false>::smem(N);
   if (nb <= 12) return SolveLaunch<0, 12, false>::smem(N);
   if (use_v2(nb))
@@ -1293,11 +1301,8 @@ eb_status eb_target_fill_host(int device, int ng, const double* mu, const double
 // (single-wave) batches from the group's side stream (peer_gather.cuh).  EB_GATHER_FUSE_MIN_BATCH overrides.
 extern "C" int eb_gather_fuse_min_batch(void)
 {
-  static const int v = [] {
-    const char* e = std::getenv("EB_GATHER_FUSE_MIN_BATCH");
-    return e ? std::atoi(e) : 8192;
-  }();
-  return v;
+  const char* e = std::getenv("EB_GATHER_FUSE_MIN_BATCH");  // read at every group creation (tests switch it)
+  return e ? std::atoi(e) : 8192;
 }
 
 struct eb_peer_group
@@ -2083,6 +2088,150 @@ eb_status eb_dwa_control_traj_host(eb_grid* g, const eb_collision* c, const eb_d
   const size_t ref_doubles = 3 * (size_t)ncols * (per_instance ? (size_t)std::max(count, 0) : 1);
   return dwa_host(g, c, d, x0, vb, xt_ref, ref_doubles, true, ncols, per_instance, dt_ref, count, found, u_opt,
                   min_cost);
+}
+
+// ---------------------------------------------------------------------------
+// row-sharded phi_k on several GPUs: all-reduce fused into the tile kernel (phik_tma.cuh)
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+struct eb_phik_peer
+{
+  int device = 0, rank = 0, world = 1;
+  double* recv[2] = {};                    // own receive buffers, [world][1024], alternating by step
+  unsigned long long* flags = nullptr;     // own arrival flags, [8]
+  double* peer_recv[8][2] = {};            // every rank's receive buffers as seen from here
+  unsigned long long* peer_flags[8] = {};
+  bool connected = false;
+  unsigned long long step = 0;
+};
+
+extern "C" {
+
+int eb_phik_peer_blob_bytes(void) { return 3 * (int)sizeof(cudaIpcMemHandle_t); }
+
+eb_status eb_phik_peer_create(int device, int rank, int world, eb_phik_peer** out)
+{
+  if (!out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_peer_create: out is NULL");
+  *out = nullptr;
+  if (world < 1 || world > 8 || rank < 0 || rank >= world)
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_peer_create: need 1 <= world <= 8, 0 <= rank < world");
+  EB_CUDA(cudaSetDevice(device));
+  eb_phik_peer* g = new (std::nothrow) eb_phik_peer();
+  if (!g) return fail(EB_ERR_CUDA, "out of host memory");
+  g->device = device;
+  g->rank = rank;
+  g->world = world;
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < 2 && e == cudaSuccess; k++)
+  {
+    e = cudaMalloc(&g->recv[k], sizeof(double) * 1024 * (size_t)world);
+    if (e == cudaSuccess) e = cudaMemset(g->recv[k], 0, sizeof(double) * 1024 * (size_t)world);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&g->flags, sizeof(unsigned long long) * 8);
+  if (e == cudaSuccess) e = cudaMemset(g->flags, 0, sizeof(unsigned long long) * 8);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess)
+  {
+    eb_phik_peer_destroy(g);
+    return fail(EB_ERR_CUDA, std::string("eb_phik_peer_create: ") + cudaGetErrorString(e));
+  }
+  *out = g;
+  return EB_OK;
+}
+
+eb_status eb_phik_peer_export(eb_phik_peer* g, unsigned char* blob)
+{
+  if (!g || !blob) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_peer_export: NULL argument");
+  EB_CUDA(cudaSetDevice(g->device));
+  cudaIpcMemHandle_t h[3];
+  EB_CUDA(cudaIpcGetMemHandle(&h[0], g->recv[0]));
+  EB_CUDA(cudaIpcGetMemHandle(&h[1], g->recv[1]));
+  EB_CUDA(cudaIpcGetMemHandle(&h[2], g->flags));
+  std::memcpy(blob, h, sizeof(h));
+  return EB_OK;
+}
+
+eb_status eb_phik_peer_connect(eb_phik_peer* g, const unsigned char* blobs)
+{
+  if (!g || (g->world > 1 && !blobs)) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_peer_connect: NULL argument");
+  EB_CUDA(cudaSetDevice(g->device));
+  for (int r = 0; r < g->world; r++)
+  {
+    if (r == g->rank)
+    {
+      g->peer_recv[r][0] = g->recv[0];
+      g->peer_recv[r][1] = g->recv[1];
+      g->peer_flags[r] = g->flags;
+      continue;
+    }
+    cudaIpcMemHandle_t h[3];
+    std::memcpy(h, blobs + (size_t)r * sizeof(h), sizeof(h));
+    void* ptr[3] = {};
+    for (int k = 0; k < 3; k++)
+    {
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr[k], h[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return fail(EB_ERR_CUDA, std::string("eb_phik_peer_connect: cudaIpcOpenMemHandle (peer access over NVLink is "
+                                             "required): ") + cudaGetErrorString(e));
+    }
+    g->peer_recv[r][0] = static_cast<double*>(ptr[0]);
+    g->peer_recv[r][1] = static_cast<double*>(ptr[1]);
+    g->peer_flags[r] = static_cast<unsigned long long*>(ptr[2]);
+  }
+  g->connected = true;
+  return EB_OK;
+}
+
+void eb_phik_peer_destroy(eb_phik_peer* g)
+{
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  if (g->connected)
+    for (int r = 0; r < g->world; r++)
+      if (r != g->rank)
+      {
+        cudaIpcCloseMemHandle(g->peer_recv[r][0]);
+        cudaIpcCloseMemHandle(g->peer_recv[r][1]);
+        cudaIpcCloseMemHandle(g->peer_flags[r]);
+      }
+  cudaFree(g->recv[0]);
+  cudaFree(g->recv[1]);
+  cudaFree(g->flags);
+  delete g;
+}
+
+// COLLECTIVE: every rank of the group calls this once per step with its own row block (a plan made by
+// eb_phik_plan_create_rows).  One kernel per rank; the normalised coefficients of the WHOLE grid land in phik_dev on
+// every rank, bit-identical.  Needs the TMA tile kernel (even nx >= 64, 16-byte aligned density).
+eb_status eb_phik_execute_allreduce_dev(eb_phik_plan* p, eb_phik_peer* g, const double* phi_dev, double* phik_dev,
+                                        double* phi_sum_dev)
+{
+  EB_TRACE("eb_phik_execute_allreduce_dev");
+  if (!p || !g || !phi_dev || !phik_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_execute_allreduce_dev: NULL argument");
+  if (!g->connected) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_execute_allreduce_dev: peer group is not connected");
+  if (!eb::phik_tma_supported(p->nx, p->ny) || !eb::phik_tma_encoder() || (reinterpret_cast<uintptr_t>(phi_dev) & 15) != 0)
+    return fail(EB_ERR_UNSUPPORTED, "eb_phik_execute_allreduce_dev: needs the TMA tile kernel (even nx >= 64, aligned density)");
+  const int par = (int)(g->step & 1);
+  eb::PhikTmaPeer pp;
+  pp.n_peer = g->world;
+  for (int r = 0; r < g->world; r++)
+  {
+    pp.peer_recv[r] = g->peer_recv[r][par] + (size_t)g->rank * 1024;
+    pp.peer_flag[r] = g->peer_flags[r] + g->rank;
+  }
+  pp.my_flags = g->flags;
+  pp.my_recv = g->recv[par];
+  pp.step = g->step + 1;
+  const int saved = p->algo;
+  p->algo = p->algo == 5 ? 5 : 4;
+  p->peer = &pp;
+  const eb_status st = phik_execute(p, phi_dev, phik_dev, phi_sum_dev, nullptr);
+  p->peer = nullptr;
+  p->algo = saved;
+  if (st == EB_OK) g->step += 1;
+  return st;
 }
 
 // ---------------------------------------------------------------------------

@@ -94,6 +94,18 @@ struct PhikTmaParams
   unsigned int* done;  // arrival counter, zero between launches
   int nb, fold;
   double *phik, *phi_sum, *raw;  // any may be null
+  // Row-sharded grids on several GPUs: the all-reduce of the ranks' raw 32 x 32 blocks is part
+  // of THIS kernel.  The last CTA stores its block into every rank's receive buffer over NVLink peer memory (slot =
+  // this rank), raises this rank's flag on every peer after a system-scope fence, waits for the other ranks' flags
+  // and sums the slots in rank order -- identical bits on every rank, no NCCL call, no second launch.  Two receive
+  // buffers alternate by step: a rank can start step s + 2 only after every peer has finished step s + 1, i.e. is
+  // past its reads of step s.
+  int n_peer;                                  // 0: single GPU
+  double* peer_recv[8];                        // rank q's receive buffer of this step's parity, offset to this rank's slot
+  unsigned long long* peer_flag[8];            // this rank's slot in rank q's arrival flags
+  const unsigned long long* my_flags;          // [n_peer]
+  const double* my_recv;                       // this rank's receive buffer of this step's parity, [n_peer][1024]
+  unsigned long long step;                     // 1-based step number = flag value
 };
 
 template <bool FOLD>
@@ -313,24 +325,49 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   if (!s_last) return;
   __threadfence();  // the other CTAs' partials, released before their counter increments
   const int nparts = (int)gridDim.x;
-  double sum2[2];
-#pragma unroll
-  for (int h = 0; h < 2; h++)
+  // 16 loads per output in flight (the partials sit in L2: the sum is latency-bound); the ORDER of the additions is fixed
+  double sum2[2] = { 0.0, 0.0 };
+  for (int p0 = 0; p0 < nparts; p0 += 8)
   {
-    const int t = threadIdx.x + h * (kPtWarps * 32);
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four loads in flight; the ORDER of the additions is fixed
-    int pth = 0;
-    double acc = 0.0;
-    for (; pth + 4 <= nparts; pth += 4)
+    double v[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+        v[h][j] = p0 + j < nparts ? __ldcg(p.parts + (size_t)(p0 + j) * 1024 + threadIdx.x + h * (kPtWarps * 32)) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
     {
-      a0 = __ldcg(p.parts + (size_t)(pth + 0) * 1024 + t);
-      a1 = __ldcg(p.parts + (size_t)(pth + 1) * 1024 + t);
-      a2 = __ldcg(p.parts + (size_t)(pth + 2) * 1024 + t);
-      a3 = __ldcg(p.parts + (size_t)(pth + 3) * 1024 + t);
-      acc = (((acc + a0) + a1) + a2) + a3;
+      sum2[0] += v[0][j];
+      sum2[1] += v[1][j];
     }
-    for (; pth < nparts; pth++) acc += __ldcg(p.parts + (size_t)pth * 1024 + t);
-    sum2[h] = acc;
+  }
+  if (p.n_peer > 1)
+  {
+    // ---- fused all-reduce over NVLink peer memory ----
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+    {
+      const int t = threadIdx.x + h * (kPtWarps * 32);
+#pragma unroll
+      for (int q_ = 0; q_ < 8; q_++)
+        if (q_ < p.n_peer) p.peer_recv[q_][t] = sum2[h];  // slots keep the kernel's column order; every rank folds alike
+    }
+    __threadfence_system();
+    pt_consumer_barrier();
+    if (threadIdx.x < p.n_peer) *(volatile unsigned long long*)p.peer_flag[threadIdx.x] = p.step;
+    if (threadIdx.x < p.n_peer)
+      while (*(const volatile unsigned long long*)(p.my_flags + threadIdx.x) < p.step) __nanosleep(64);
+    pt_consumer_barrier();
+    __threadfence_system();
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+    {
+      const int t = threadIdx.x + h * (kPtWarps * 32);
+      double acc = 0.0;
+      for (int r = 0; r < p.n_peer; r++) acc += *(const volatile double*)(p.my_recv + (size_t)r * 1024 + t);  // rank order
+      sum2[h] = acc;
+    }
   }
   if (threadIdx.x == 0) s_total = sum2[0];  // order (0, 0) sits at column 0 with or without the fold
   pt_consumer_barrier();
@@ -390,11 +427,22 @@ inline bool phik_tma_make_map(const double* phi, int nx, int ny, CUtensorMap* ma
 
 // Launches one persistent CTA per SM (fewer when there is less work than that); returns the number of partial
 // blocks written (= grid size) or -1 on failure (no encoder, misaligned density, launch error).
+struct PhikTmaPeer
+{
+  int n_peer = 0;
+  double* peer_recv[8] = {};
+  unsigned long long* peer_flag[8] = {};
+  const unsigned long long* my_flags = nullptr;
+  const double* my_recv = nullptr;
+  unsigned long long step = 0;
+};
+
 struct PhikTmaOut
 {
   unsigned int* done;
   int nb;
   double *phik, *phi_sum, *raw;
+  const PhikTmaPeer* peer = nullptr;
 };
 
 template <bool FOLD>
@@ -417,6 +465,18 @@ inline int phik_tma_launch_t(const double* phi, int nx, int ny, const double* cx
   p.phik = out.phik;
   p.phi_sum = out.phi_sum;
   p.raw = out.raw;
+  if (out.peer && out.peer->n_peer > 1)
+  {
+    p.n_peer = out.peer->n_peer;
+    for (int q = 0; q < p.n_peer; q++)
+    {
+      p.peer_recv[q] = out.peer->peer_recv[q];
+      p.peer_flag[q] = out.peer->peer_flag[q];
+    }
+    p.my_flags = out.peer->my_flags;
+    p.my_recv = out.peer->my_recv;
+    p.step = out.peer->step;
+  }
   const int ncols = FOLD ? nx / 2 : nx;
   p.nchunks = (ncols + G::kCols - 1) / G::kCols;
   const int bands = (ny + kPtRows - 1) / kPtRows;

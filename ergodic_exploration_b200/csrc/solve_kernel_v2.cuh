@@ -52,8 +52,8 @@ struct Solve2Cfg
   static constexpr int kStage = 64;                        // e_x | e_y of one round, handed to the time-step lanes
   static constexpr int kTabDoubles = kUnion + kStage;
   static constexpr int kFields = 8;                        // heading cos, sin; Fourier-frame x, y; cos, sin of a x; of b y
-  static constexpr int kMinBlocks = (NB <= 16 ? EB_MINB2_16 : EB_MINB2_20) * 4 / kSolveWarps;
-  static constexpr int kWideWarps = NB <= 16 ? 24 : 16;  // one CTA per SM for single-wave batches (see SolveCfg)
+  static constexpr int kMinBlocks = (NB <= 12 ? 7 : NB <= 16 ? EB_MINB2_16 : EB_MINB2_20) * 4 / kSolveWarps;
+  static constexpr int kWideWarps = NB <= 12 ? 28 : NB <= 16 ? 24 : 16;  // one CTA per SM for single-wave batches (see SolveCfg)
 };
 
 // per-step records are kept for the horizon rounded up to a half-round (16 steps)

@@ -196,15 +196,18 @@ class PeerGather:
         return int(self._lib.eb_peer_group_steps(self._h))
 
     def control(self, grid, x: torch.Tensor, mem_idx: Optional[torch.Tensor] = None,
-                metric: Optional[torch.Tensor] = None) -> int:
+                metric: Optional[torch.Tensor] = None, ctl=None) -> int:
         """one control() step of this rank's instances; returns the step number (1-based)
-        whose gathered rows ``gathered(step)`` will hold once ``wait(step)`` has passed"""
+        whose gathered rows ``gathered(step)`` will hold once ``wait(step)`` has passed.
+        ``ctl``: another controller of the SAME batch size on this device (the group only fixes the row count)"""
         b = grid.as_tuple() if hasattr(grid, "as_tuple") else tuple(float(v) for v in grid)
-        self.ctl._sync_stream()
+        ctl = self.ctl if ctl is None else ctl
+        assert ctl.batch == self.ctl.batch and ctl.device == self.ctl.device
+        ctl._sync_stream()
         assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == 3 * self.ctl.batch
         idx_p = C.c_void_p(mem_idx.data_ptr()) if mem_idx is not None else None
         met_p = C.c_void_p(metric.data_ptr()) if metric is not None else None
-        st = self._lib.eb_control_dev_gather(self.ctl._h, self._h, *b, C.c_void_p(x.data_ptr()), idx_p, met_p)
+        st = self._lib.eb_control_dev_gather(ctl._h, self._h, *b, C.c_void_p(x.data_ptr()), idx_p, met_p)
         if st == capi.EB_ERR_INVALID_ARGUMENT:
             raise ValueError(self._lib.eb_last_error().decode())
         check(st)
@@ -220,3 +223,68 @@ class PeerGather:
         step = self.steps if step is None else step
         ptr = self._lib.eb_peer_gathered_dev(self._h, int(step))
         return torch.as_tensor(_DevView(ptr, (self.world * self.ctl.batch, 3)), device=torch.device("cuda", self.ctl.device))
+
+
+class PhikAllReduce:
+    """Row-sharded phi_k with the cross-GPU reduction fused into the tile kernel (include/ergodic_b200.h,
+    eb_phik_peer_*): every rank contracts its row block and the last CTA of its kernel exchanges the raw 32 x 32
+    blocks over NVLink peer memory -- one kernel launch per rank and step, no NCCL call on the data path.
+    Collective at construction (IPC handles through one all_gather) and in ``execute`` (every rank calls it)."""
+
+    def __init__(self, plan, group=None):
+        self._lib = capi.load()
+        self.plan, self.group = plan, group
+        multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else 0
+        h = C.c_void_p()
+        check(self._lib.eb_phik_peer_create(plan.device, self.rank, self.world, C.byref(h)))
+        self._h = h
+        nbytes = self._lib.eb_phik_peer_blob_bytes()
+        blob = (C.c_ubyte * nbytes)()
+        check(self._lib.eb_phik_peer_export(h, blob))
+        if multi:
+            dev = torch.device("cuda", plan.device)
+            mine = torch.tensor(list(bytes(blob)), dtype=torch.uint8, device=dev)
+            allb = torch.empty(self.world * nbytes, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allb, mine, group=group)
+            raw = bytes(allb.cpu().numpy().tobytes())
+            buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+            st = self._lib.eb_phik_peer_connect(h, buf)
+            ok = torch.tensor([1 if st == capi.EB_OK else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                msg = self._lib.eb_last_error().decode(errors="replace") if st != capi.EB_OK else "failed on another rank"
+                self._lib.eb_phik_peer_destroy(h)
+                self._h = None
+                raise RuntimeError(f"peer mapping: {msg}")
+        else:
+            check(self._lib.eb_phik_peer_connect(h, None))
+
+    def execute(self, phi: torch.Tensor, phik: Optional[torch.Tensor] = None, phi_sum: Optional[torch.Tensor] = None):
+        """phi: this rank's (rows, nx) block; returns the (nb * nb,) coefficients of the WHOLE grid (every rank alike)"""
+        s = torch.cuda.current_stream(self.plan.device).cuda_stream
+        check(self._lib.eb_phik_plan_set_stream(self.plan._h, C.c_void_p(s)))
+        assert phi.is_cuda and phi.dtype == torch.float64 and phi.is_contiguous() and phi.numel() == self.plan.nx * self.plan.ny
+        if phik is None:
+            phik = torch.empty(self.plan.nb * self.plan.nb, dtype=torch.float64, device=phi.device)
+        sp = C.c_void_p(phi_sum.data_ptr()) if phi_sum is not None else None
+        check(self._lib.eb_phik_execute_allreduce_dev(self.plan._h, self._h, C.c_void_p(phi.data_ptr()),
+                                                      C.c_void_p(phik.data_ptr()), sp))
+        return phik
+
+    def close(self):
+        if getattr(self, "_h", None):
+            if dist.is_initialized() and self.world > 1:
+                torch.cuda.synchronize(self.plan.device)
+                dist.barrier(group=self.group)  # nobody is still storing into a buffer about to be freed
+            self._lib.eb_phik_peer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self.world == 1:
+                self._lib.eb_phik_peer_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

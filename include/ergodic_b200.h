@@ -323,6 +323,20 @@ eb_status eb_dwa_control_traj_dev(eb_grid *g, const eb_collision *c, const eb_dw
                                   const double *vb_dev, const double *xt_ref_dev, int ncols, int per_instance,
                                   double dt_ref, int count, int *found_dev, double *u_opt_dev, double *min_cost_dev);
 
+/* ---- row-sharded phi_k on several GPUs -----------------------
+ * The all-reduce of the ranks' raw 32 x 32 blocks is fused into the tile kernel: the last CTA of every rank stores its
+ * block into all ranks' receive buffers over NVLink peer memory (CUDA IPC mappings, exchanged once like eb_peer_group),
+ * raises an arrival flag, waits for the others' and sums the slots in rank order.  eb_phik_execute_allreduce_dev is a
+ * COLLECTIVE call: every rank of the group makes it once per step with a plan of its own row block. */
+typedef struct eb_phik_peer eb_phik_peer;
+int eb_phik_peer_blob_bytes(void);
+eb_status eb_phik_peer_create(int device, int rank, int world, eb_phik_peer **out);
+eb_status eb_phik_peer_export(eb_phik_peer *g, unsigned char *blob);
+eb_status eb_phik_peer_connect(eb_phik_peer *g, const unsigned char *blobs /* world blobs, rank order */);
+void eb_phik_peer_destroy(eb_phik_peer *g);
+eb_status eb_phik_execute_allreduce_dev(eb_phik_plan *p, eb_phik_peer *g, const double *phi_dev, double *phik_dev,
+                                        double *phi_sum_dev /* may be NULL */);
+
 /* ---- map-derived target ------------------------------
  * Density from an occupancy grid: Phi[i][j] = entropy(cell / 100) (numerics.hpp:164-179 over GridMap::getCell,
  * grid.cpp:177-184; -1 = unknown), sampled at the cell centres of the map frame [0, xsize * res] x [0, ysize * res],
