@@ -403,8 +403,7 @@ def bench_solve(ctx, key, steps, warmup, with_cpu=True):
     def step_dev(i):
         c_ = ctls[i % n_rot]
         if pg is not None:
-            s = pg.control(BOUNDS, xd, metric=metd, ctl=c_)
-            pg.wait(s)
+            pg.control_wait(BOUNDS, xd, metric=metd, ctl=c_)  # solve + gather + wait for every rank's rows
         else:
             c_.control(BOUNDS, xd, u0=u0d, metric=metd)
 
@@ -484,8 +483,7 @@ def bench_solve(ctx, key, steps, warmup, with_cpu=True):
 
         def step_e2e():
             xd.copy_(xh, non_blocking=True)
-            s = pg.control(BOUNDS, xd, metric=metd)
-            pg.wait(s)
+            s = pg.control_wait(BOUNDS, xd, metric=metd)
             gh.copy_(pg.gathered(s), non_blocking=True)
             torch.cuda.current_stream().synchronize()
         d2h = world * B * 24
@@ -579,8 +577,7 @@ def bench_loop(ctx, loop_steps, warmup):
     def tick():
         ctl.addStateMemory(xd)  # exploration.hpp:209
         if pg is not None:
-            step = pg.control(BOUNDS, xd, metric=metd)
-            pg.wait(step)
+            step = pg.control_wait(BOUNDS, xd, metric=metd)
             mine = pg.gathered(step)[rank * B:(rank + 1) * B]
             eb.integrate_twist(xd, mine, DT, out=xd)
             return step

@@ -143,6 +143,7 @@ SIGNATURES = {
     "eb_peer_group_destroy": (None, [_vp]),
     "eb_control_dev_gather": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp]),
     "eb_peer_group_wait": (C.c_int, [_vp, _vp, C.c_ulonglong]),
+    "eb_control_dev_gather_wait": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp]),
     "eb_peer_gathered_dev": (_vp, [_vp, C.c_ulonglong]),
     "eb_peer_group_steps": (C.c_ulonglong, [_vp]),
     "eb_peer_group_fused": (C.c_int, [_vp, C.c_int]),

@@ -1321,6 +1321,7 @@ struct eb_peer_group
   cudaStream_t side = nullptr;
   cudaEvent_t solved[eb::kPeerBuffers] = {}, published[eb::kPeerBuffers] = {};
   unsigned int* side_counter = nullptr;
+  bool side_used = false;                       // a side-stream publication has been enqueued at least once
   int fuse_min_batch = eb_gather_fuse_min_batch();  // batches at least this large publish from inside the solve kernel
 };
 
@@ -1493,6 +1494,7 @@ eb_status eb_control_dev_gather(eb_controller* c, eb_peer_group* g, double xmin,
     // into the spare slots, or that kernel spills into a second wave.
     const int blocks = (int)std::max<long long>(1, std::min<long long>(4, (g->elems / 2 + 4095) / 4096));
     eb::peer_publish_kernel<<<blocks, 256, 0, g->side>>>(pp);
+    g->side_used = true;
     EB_CUDA(cudaGetLastError());
     EB_CUDA(cudaEventRecord(g->published[parity], g->side));
     c->launches += 1;
@@ -1515,6 +1517,53 @@ eb_status eb_control_dev_gather(eb_controller* c, eb_peer_group* g, double xmin,
   c->peer = nullptr;
   if (st == EB_OK) g->step += 1;
   return st;
+}
+
+// control() + gather + wait in one call, everything on the controller's stream: when it returns (stream order), the
+// rows of EVERY rank for this step are in eb_peer_gathered_dev(g, step).  Single-wave batches publish and wait in one
+// kernel behind the solve kernel (peer_publish_wait_kernel); larger ones publish from inside the solve kernel and
+// enqueue the wait kernel.
+eb_status eb_control_dev_gather_wait(eb_controller* c, eb_peer_group* g, double xmin, double xmax, double ymin, double ymax,
+                                     const double* x_dev, const int* mem_idx_dev, double* metric_dev)
+{
+  EB_TRACE("eb_control_dev_gather_wait");
+  if (!c || !g) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather_wait: NULL argument");
+  if (!g->connected) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather_wait: peer group is not connected");
+  if (g->elems != 3LL * c->B) return fail(EB_ERR_INVALID_ARGUMENT, "eb_control_dev_gather_wait: peer group sized for another batch");
+  if (c->B >= g->fuse_min_batch)
+  {
+    eb_status st = eb_control_dev_gather(c, g, xmin, xmax, ymin, ymax, x_dev, mem_idx_dev, metric_dev);
+    if (st != EB_OK) return st;
+    return eb_peer_group_wait(g, c, g->step);
+  }
+  EB_CUDA(cudaSetDevice(g->device));
+  const int parity = (int)(g->step % eb::kPeerBuffers);
+  const unsigned long long need =
+      g->step + 2 > (unsigned long long)eb::kPeerBuffers ? g->step + 2 - eb::kPeerBuffers : 0;
+  // a side-stream publication of an earlier step (mixed use of the two entry points) must have left this buffer
+  if (g->step >= (unsigned long long)eb::kPeerBuffers && g->side_used)
+    EB_CUDA(cudaStreamWaitEvent(c->stream, g->published[parity], 0));
+  const eb_status st = eb_control_dev(c, xmin, xmax, ymin, ymax, x_dev, mem_idx_dev, g->local_u0[parity], metric_dev);
+  if (st != EB_OK) return st;
+  eb::PublishParams pp{};
+  pp.src = g->local_u0[parity];
+  pp.elems = g->elems;
+  pp.n_peer = g->world;
+  for (int r = 0; r < g->world; r++)
+  {
+    pp.dst[r] = g->peer_gathered[r][parity] + (size_t)g->rank * (size_t)g->elems;
+    pp.flag[r] = g->peer_flags[r] + g->rank;
+  }
+  pp.flag_value = g->step + 1;
+  pp.my_flags = g->flags;
+  pp.need = need;
+  pp.done_counter = g->counter;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(64, (g->elems / 2 + 255) / 256));
+  eb::peer_publish_wait_kernel<<<blocks, 256, 0, c->stream>>>(pp);
+  EB_CUDA(cudaGetLastError());
+  c->launches += 1;
+  g->step += 1;
+  return EB_OK;
 }
 
 // enqueues (on the controller's stream) a wait until every rank's rows of step `step` have arrived here

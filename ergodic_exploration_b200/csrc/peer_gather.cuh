@@ -73,6 +73,45 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(const PublishParams p
   }
 }
 
+// Synchronous form for single-wave batches: publish AND wait in one kernel on the controller's own stream, right
+// behind the solve kernel -- no side-stream hop, no second launch.  Nothing else needs the SMs between the solve
+// kernel and the consumer of the gathered rows, so the copy uses many blocks; the last block to finish its stores
+// fences, raises this rank's flags on every peer and then waits for the peers' flags.
+__global__ void __launch_bounds__(256) peer_publish_wait_kernel(const PublishParams p)
+{
+  if (threadIdx.x < p.n_peer)
+    while (*(const volatile unsigned long long*)(p.my_flags + threadIdx.x) < p.need) __nanosleep(100);
+  __syncthreads();
+  const long long pairs = p.elems >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (long long)gridDim.x * blockDim.x)
+  {
+    const double2 v = reinterpret_cast<const double2*>(p.src)[i];
+    for (int q = 0; q < p.n_peer; q++) reinterpret_cast<double2*>(p.dst[q])[i] = v;
+  }
+  if ((p.elems & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+    for (int q = 0; q < p.n_peer; q++) p.dst[q][p.elems - 1] = p.src[p.elems - 1];
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last;
+  if (threadIdx.x == 0)
+  {
+    const unsigned int prev = atomicAdd(p.done_counter, 1u);
+    s_last = prev == gridDim.x - 1 ? 1u : 0u;
+    if (s_last)
+    {
+      *p.done_counter = 0u;
+      __threadfence_system();
+      for (int q = 0; q < p.n_peer; q++) *(volatile unsigned long long*)p.flag[q] = p.flag_value;
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x < p.n_peer)
+    while (*(const volatile unsigned long long*)(p.my_flags + threadIdx.x) < p.flag_value) __nanosleep(64);
+  __syncthreads();
+  __threadfence_system();  // acquire: the peers' rows are visible to what follows on this stream
+}
+
 // spins (one thread) until every rank's arrival flag has reached `step`
 __global__ void peer_wait_kernel(const volatile unsigned long long* flags, int world, unsigned long long step)
 {

@@ -213,6 +213,23 @@ class PeerGather:
         check(st)
         return self.steps
 
+    def control_wait(self, grid, x: torch.Tensor, mem_idx: Optional[torch.Tensor] = None,
+                     metric: Optional[torch.Tensor] = None, ctl=None) -> int:
+        """control() + gather + wait as one stream-ordered operation (eb_control_dev_gather_wait): when the work
+        enqueued by this call has run, ``gathered(step)`` holds every rank's rows.  Returns the step number."""
+        b = grid.as_tuple() if hasattr(grid, "as_tuple") else tuple(float(v) for v in grid)
+        ctl = self.ctl if ctl is None else ctl
+        assert ctl.batch == self.ctl.batch and ctl.device == self.ctl.device
+        ctl._sync_stream()
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == 3 * self.ctl.batch
+        idx_p = C.c_void_p(mem_idx.data_ptr()) if mem_idx is not None else None
+        met_p = C.c_void_p(metric.data_ptr()) if metric is not None else None
+        st = self._lib.eb_control_dev_gather_wait(ctl._h, self._h, *b, C.c_void_p(x.data_ptr()), idx_p, met_p)
+        if st == capi.EB_ERR_INVALID_ARGUMENT:
+            raise ValueError(self._lib.eb_last_error().decode())
+        check(st)
+        return self.steps
+
     def wait(self, step: Optional[int] = None) -> None:
         """enqueue (on the current stream) a wait until every rank's rows of ``step`` are here"""
         self.ctl._sync_stream()

@@ -246,6 +246,11 @@ void eb_peer_group_destroy(eb_peer_group *g);
 eb_status eb_control_dev_gather(eb_controller *c, eb_peer_group *g, double xmin, double xmax, double ymin,
                                 double ymax, const double *x_dev, const int *mem_idx_dev, double *metric_dev);
 eb_status eb_peer_group_wait(eb_peer_group *g, eb_controller *c, unsigned long long step);
+/* control() + gather + wait as ONE stream-ordered operation on the controller's stream: afterwards the rows of every rank
+ * for this step are in eb_peer_gathered_dev(g, eb_peer_group_steps(g)).  The form a closed loop wants (every tick needs
+ * the complete step); single-wave batches publish and wait in one kernel right behind the solve kernel. */
+eb_status eb_control_dev_gather_wait(eb_controller *c, eb_peer_group *g, double xmin, double xmax, double ymin,
+                                     double ymax, const double *x_dev, const int *mem_idx_dev, double *metric_dev);
 double *eb_peer_gathered_dev(eb_peer_group *g, unsigned long long step);
 unsigned long long eb_peer_group_steps(const eb_peer_group *g);
 /* 1: a batch of this size publishes from inside the solve kernel, 0: from the group's side stream */

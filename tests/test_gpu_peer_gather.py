@@ -61,9 +61,12 @@ ctl = make_gpu(MODEL_OMNI, B, device=rank)
 ctl.set_ut(warm_ut(rng, B, 50, MODEL_OMNI))
 pg = PeerGather(ctl)
 x = torch.from_numpy(random_states(rng, B)).cuda()
-for step in range(1, 12):
-    pg.control(BOUNDS_10, x)
-    pg.wait(step)
+for step in range(1, 14):
+    if step % 3 == 0:   # the one-call form: solve + gather + wait on the controller's stream
+        assert pg.control_wait(BOUNDS_10, x) == step
+    else:
+        pg.control(BOUNDS_10, x)
+        pg.wait(step)
     torch.cuda.synchronize()
     g = pg.gathered(step)
     ref = torch.empty_like(g)
