@@ -198,7 +198,7 @@ eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin
   p->ly = ly;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  p->max_parts = std::max(1, sms);
+  p->max_parts = std::min(std::max(1, sms), eb::kPtGroup * eb::kPtMaxGroups);
   const std::vector<double> xs = accumulated_axis(nx, resolution, x_first);
   const std::vector<double> ys_all = accumulated_axis(row_begin + ny, resolution, y_first);
   const std::vector<double> ys(ys_all.begin() + row_begin, ys_all.end());
@@ -218,11 +218,12 @@ eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin
   EB_CUDA_P(cudaMalloc(&p->d_cx, sizeof(double) * (size_t)nx * eb::kPhikLd));
   EB_CUDA_P(cudaMalloc(&p->d_cy, sizeof(double) * (size_t)ny * eb::kPhikLd));
   EB_CUDA_P(cudaMalloc(&p->d_T, sizeof(double) * (size_t)ny * eb::kPhikLd));
-  EB_CUDA_P(cudaMalloc(&p->d_parts, sizeof(double) * 1024 * (size_t)p->max_parts));
+  // per-CTA blocks + the per-group sums of the TMA kernel's two-level final sum
+  EB_CUDA_P(cudaMalloc(&p->d_parts, sizeof(double) * 1024 * (size_t)(p->max_parts + eb::kPtMaxGroups)));
   EB_CUDA_P(cudaMalloc(&p->d_phik, sizeof(double) * 1024));
   EB_CUDA_P(cudaMalloc(&p->d_sum, sizeof(double)));
-  EB_CUDA_P(cudaMalloc(&p->d_done, sizeof(unsigned int)));
-  EB_CUDA_P(cudaMemset(p->d_done, 0, sizeof(unsigned int)));
+  EB_CUDA_P(cudaMalloc(&p->d_done, sizeof(unsigned int) * (1 + eb::kPtMaxGroups)));
+  EB_CUDA_P(cudaMemset(p->d_done, 0, sizeof(unsigned int) * (1 + eb::kPtMaxGroups)));
   EB_CUDA_P(cudaMemcpy(p->d_xs, xs.data(), sizeof(double) * nx, cudaMemcpyHostToDevice));
   EB_CUDA_P(cudaMemcpy(p->d_ys, ys.data(), sizeof(double) * ny, cudaMemcpyHostToDevice));
   // basis.cpp:85: cos(k * (PI / l) * x)

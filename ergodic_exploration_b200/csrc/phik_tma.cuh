@@ -76,6 +76,8 @@ __device__ __forceinline__ void tma_tile_g2s(void* dst, const CUtensorMap* map, 
       "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+constexpr int kPtGroup = 13;       // CTAs per first-level group of the fused final sum
+constexpr int kPtMaxGroups = 63;   // counters: 1 + kPtMaxGroups
 __device__ __forceinline__ void pt_consumer_barrier()
 {
   asm volatile("bar.sync 1, %0;" ::"n"(kPtWarps * 32) : "memory");
@@ -85,13 +87,13 @@ struct PhikTmaParams
 {
   const double* cxp;   // permuted C_x, [nchunks * kCols][36]
   const double* cy;    // C_y, [ny][32]
-  double* parts;       // [gridDim.x][1024]
+  double* parts;       // [gridDim.x + groups][1024]: per-CTA blocks, then the per-group sums
   int nx, ny;
   int nchunks;         // stages per band
   long long total;     // bands * nchunks
   // fused final reduction: the last CTA to finish sums the per-CTA partials in index order (deterministic),
   // undoes the fold's order permutation and normalises by raw[0][0] = sum(Phi)
-  unsigned int* done;  // arrival counter, zero between launches
+  unsigned int* done;  // arrival counters, zero between launches: [0] groups finished, [1 + g] CTAs of group g finished
   int nb, fold;
   double *phik, *phi_sum, *raw;  // any may be null
   // Row-sharded grids on several GPUs: the all-reduce of the ranks' raw 32 x 32 blocks is part
@@ -106,7 +108,23 @@ struct PhikTmaParams
   const unsigned long long* my_flags;          // [n_peer]
   const double* my_recv;                       // this rank's receive buffer of this step's parity, [n_peer][1024]
   unsigned long long step;                     // 1-based step number = flag value
+  unsigned long long* trace;                   // EB_PT_TRACE builds: [gridDim.x][8] globaltimer stamps, else null
 };
+
+#ifdef EB_PT_TRACE
+__device__ __forceinline__ void pt_stamp(const PhikTmaParams& p, int slot)
+{
+  if (threadIdx.x == 0 && p.trace)
+  {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.trace[blockIdx.x * 8 + slot] = t;
+  }
+}
+#define PT_STAMP(slot) pt_stamp(p, slot)
+#else
+#define PT_STAMP(slot)
+#endif
 
 template <bool FOLD>
 __global__ void __launch_bounds__(kPtThreads, 1)
@@ -121,6 +139,7 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   uint64_t* const empty = full + G::kStages;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  PT_STAMP(0);
   if (threadIdx.x == 0)
   {
     for (int s = 0; s < G::kStages; s++)
@@ -191,6 +210,10 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   {
     const int s = it % G::kStages;
     mbar_wait(&full[s], (it / G::kStages) & 1);
+#ifdef EB_PT_TRACE
+    if (it == 0) PT_STAMP(1);
+    if (it + 1 == total_it) PT_STAMP(2);
+#endif
     const unsigned char* const st = base + s * G::kStageBytes;
     const double* const cxs = reinterpret_cast<const double*>(st + G::kPhiBytes);
     if (FOLD)
@@ -264,6 +287,17 @@ __global__ void __launch_bounds__(kPtThreads, 1)
       // End of the band (or of this CTA's range): sum the four column quarters' tiles in the stage, fixed order
       // (C layout: DMMA row g <-> band row 16 rb + 8 r + rho, cols 8 t + 2 q + e), then fold with C_y.
       k = 0;
+      // warp w owns output tile (m, t) = (w / 4, w % 4) of the fold with C_y below; its C_y operands are fetched now so
+      // that their L2 latency hides behind the four turns (the last band end of a CTA is on the kernel's critical path)
+      const int m = warp >> 2, t = warp & 3;
+      const int r0 = band * kPtRows;
+      double cya[kPtRows / 4];
+#pragma unroll
+      for (int h = 0; h < kPtRows / 4; h++)
+      {
+        const int r = r0 + 4 * h + q;
+        cya[h] = r < p.ny ? __ldg(p.cy + (size_t)r * 32 + 8 * m + g) : 0.0;
+      }
 #pragma unroll 1
       for (int turn = 0; turn < 4; turn++)
       {
@@ -274,40 +308,37 @@ __global__ void __launch_bounds__(kPtThreads, 1)
           {
             double* trow = tstage + (16 * rb + 8 * r + rho) * kPtTPitch + 2 * q;
 #pragma unroll
-            for (int t = 0; t < 4; t++)
+            for (int t_ = 0; t_ < 4; t_++)
             {
               if (turn == 0)
               {
-                trow[8 * t + 0] = T[r][t][0];
-                trow[8 * t + 1] = T[r][t][1];
+                trow[8 * t_ + 0] = T[r][t_][0];
+                trow[8 * t_ + 1] = T[r][t_][1];
               }
               else
               {
-                trow[8 * t + 0] += T[r][t][0];
-                trow[8 * t + 1] += T[r][t][1];
+                trow[8 * t_ + 0] += T[r][t_][0];
+                trow[8 * t_ + 1] += T[r][t_][1];
               }
-              T[r][t][0] = T[r][t][1] = 0.0;
+              T[r][t_][0] = T[r][t_][1] = 0.0;
             }
           }
         }
         pt_consumer_barrier();
       }
-      // warp w owns output tile (m, t) = (w / 4, w % 4):  P[8m + g][8t + 2q + e] += sum_rows C_y[row][8m + g] T[row][8t + ..]
-      const int m = warp >> 2, t = warp & 3;
-      const int r0 = band * kPtRows;
-#pragma unroll 4
+      // P[8m + g][8t + 2q + e] += sum_rows C_y[row][8m + g] T[row][8t + ..]
+#pragma unroll
       for (int h = 0; h < kPtRows / 4; h++)
       {
-        const int r = r0 + 4 * h + q;
-        const double a = r < p.ny ? __ldg(p.cy + (size_t)r * 32 + 8 * m + g) : 0.0;
         const double b = tstage[(4 * h + q) * kPtTPitch + 8 * t + g];
-        dmma884(P[0], P[1], a, b);
+        dmma884(P[0], P[1], cya[h], b);
       }
       band++;
       pt_consumer_barrier();  // the T stage may be overwritten by the next band
     }
   }
 
+  PT_STAMP(3);
   {
     // with the fold the partial's columns are in [even orders | odd orders] order; the final sum undoes it
     const int m = warp >> 2, t = warp & 3;
@@ -315,32 +346,63 @@ __global__ void __launch_bounds__(kPtThreads, 1)
     out[0] = P[0];
     out[1] = P[1];
   }
-  // ---- last CTA: final sum over the partials (what phik_finalize did as a second launch) ----
+  // ---- final sum over the partials, fused (what phik_finalize did as a second launch) ----
+  // One SM summing every CTA's block is a serial tail of ~10 us (1.2 MB through one SM, 19 dependent rounds of L2
+  // latency), so the sum has two levels: the last CTA to finish in each group of kPtGroup sums that group's blocks in
+  // index order, and the last group to finish sums the group blocks in group order.  Who does the work depends on
+  // timing, the ORDER of the additions does not: the result is deterministic.
   __shared__ unsigned int s_last;
   __shared__ double s_total;
+  const int nparts = (int)gridDim.x;
+#ifdef EB_PT_FLATSUM
+  const int ngroups = 1, g_lo = 0, g_n = nparts, grp = 0;
+#else
+  const int ngroups = (nparts + kPtGroup - 1) / kPtGroup;
+  const int grp = (int)blockIdx.x / kPtGroup, g_lo = grp * kPtGroup, g_n = min(kPtGroup, nparts - g_lo);
+#endif
   __threadfence();
   pt_consumer_barrier();
-  if (threadIdx.x == 0) s_last = atomicAdd(p.done, 1u) == gridDim.x - 1 ? 1u : 0u;
+  if (threadIdx.x == 0) s_last = atomicAdd(p.done + 1 + grp, 1u) == (unsigned)(g_n - 1) ? 1u : 0u;
   pt_consumer_barrier();
+  PT_STAMP(4);
   if (!s_last) return;
   __threadfence();  // the other CTAs' partials, released before their counter increments
-  const int nparts = (int)gridDim.x;
-  // 16 loads per output in flight (the partials sit in L2: the sum is latency-bound); the ORDER of the additions is fixed
   double sum2[2] = { 0.0, 0.0 };
-  for (int p0 = 0; p0 < nparts; p0 += 8)
-  {
-    double v[2][8];
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-#pragma unroll
-      for (int h = 0; h < 2; h++)
-        v[h][j] = p0 + j < nparts ? __ldcg(p.parts + (size_t)(p0 + j) * 1024 + threadIdx.x + h * (kPtWarps * 32)) : 0.0;
-#pragma unroll
-    for (int j = 0; j < 8; j++)
+  // 2 * kPtGroup loads per thread in flight (the partials sit in L2: the sum is latency-bound); 148 CTAs = 12 groups of
+  // 13: one round of L2 latency per level
+  auto sum_blocks = [&](const double* src, int n) {
+    sum2[0] = sum2[1] = 0.0;
+    for (int p0 = 0; p0 < n; p0 += kPtGroup)
     {
-      sum2[0] += v[0][j];
-      sum2[1] += v[1][j];
+      double v[2][kPtGroup];
+#pragma unroll
+      for (int j = 0; j < kPtGroup; j++)
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+          v[h][j] = p0 + j < n ? __ldcg(src + (size_t)(p0 + j) * 1024 + threadIdx.x + h * (kPtWarps * 32)) : 0.0;
+#pragma unroll
+      for (int j = 0; j < kPtGroup; j++)
+      {
+        sum2[0] += v[0][j];
+        sum2[1] += v[1][j];
+      }
     }
+  };
+  sum_blocks(p.parts + (size_t)g_lo * 1024, g_n);
+  if (ngroups > 1)
+  {
+    double* gout = p.parts + (size_t)(nparts + grp) * 1024;
+    gout[threadIdx.x] = sum2[0];
+    gout[threadIdx.x + kPtWarps * 32] = sum2[1];
+    __threadfence();
+    pt_consumer_barrier();
+    if (threadIdx.x == 0) s_last = atomicAdd(p.done, 1u) == (unsigned)(ngroups - 1) ? 1u : 0u;
+    pt_consumer_barrier();
+    PT_STAMP(5);
+    if (!s_last) return;
+    __threadfence();
+    sum_blocks(p.parts + (size_t)nparts * 1024, ngroups);
+    PT_STAMP(6);
   }
   if (p.n_peer > 1)
   {
@@ -380,11 +442,9 @@ __global__ void __launch_bounds__(kPtThreads, 1)
     if (p.raw) p.raw[ky * 32 + kx] = (ky < p.nb && kx < p.nb) ? sum2[h] : 0.0;
     if (p.phik && ky < p.nb && kx < p.nb) p.phik[ky * p.nb + kx] = sum2[h] / s_total;
   }
-  if (threadIdx.x == 0)
-  {
-    if (p.phi_sum) *p.phi_sum = s_total;
-    *p.done = 0u;  // ready for the next launch
-  }
+  if (threadIdx.x == 0 && p.phi_sum) *p.phi_sum = s_total;
+  if (threadIdx.x <= ngroups) p.done[threadIdx.x] = 0u;  // every counter is complete by now: ready for the next launch
+  PT_STAMP(7);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
@@ -491,8 +551,39 @@ inline int phik_tma_launch_t(const double* phi, int nx, int ny, const double* cx
       return -1;
     configured[dev & 63] = true;
   }
+#ifdef EB_PT_TRACE
+  // debug build: per-CTA time line of every launch, summarised on stderr (synchronises; not for timing runs)
+  static unsigned long long* d_trace = nullptr;
+  if (!d_trace) cudaMalloc(&d_trace, sizeof(unsigned long long) * 8 * 1024);
+  cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * 8 * 1024, stream);
+  p.trace = d_trace;
+#endif
   phik_tma_kernel<FOLD><<<grid, kPtThreads, G::kSmemBytes, stream>>>(map, p);
   if (cudaGetLastError() != cudaSuccess) return -1;
+#ifdef EB_PT_TRACE
+  {
+    static unsigned long long h[8 * 1024];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, d_trace, sizeof(unsigned long long) * 8 * grid, cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int b = 0; b < grid; b++) t0 = std::min(t0, h[b * 8]);
+    static const char* names[8] = { "entry", "first stage full", "last stage full", "loop done", "group counter", "top counter",
+                                    "top sum done", "exit" };
+    fprintf(stderr, "[phik trace] grid %d rows %d\n", grid, ny);
+    for (int s = 0; s < 8; s++)
+    {
+      double lo = 1e30, hi = -1, sum = 0;
+      int n = 0;
+      for (int b = 0; b < grid; b++)
+        if (h[b * 8 + s])
+        {
+          const double t = (double)(h[b * 8 + s] - t0) * 1e-3;
+          lo = std::min(lo, t), hi = std::max(hi, t), sum += t, n++;
+        }
+      if (n) fprintf(stderr, "  %-18s n %3d  min %8.2f  mean %8.2f  max %8.2f us\n", names[s], n, lo, sum / n, hi);
+    }
+  }
+#endif
   return grid;
 }
 
