@@ -1056,13 +1056,15 @@ def run_ours(args):
     for key in order:
         try:
             if key == "c3":
-                r = bench_phik(ctx, args.steps, args.warmup)
+                # secondary line of the full run: at least 100 steps (10 ms) inside its one event pair, whatever K the
+                # primary was given -- the pair's own cost would otherwise be several per cent of 20 x 0.1 ms
+                r = bench_phik(ctx, max(args.steps, 100) if args.workload == "all" else args.steps, args.warmup)
             elif key == "c5loop":
                 r = bench_loop(ctx, args.loop_steps, args.warmup)
             elif key in ("collide", "dwa"):
                 r = bench_avoid(ctx, key, args.steps, args.warmup)
             elif key == "entropy":
-                r = bench_entropy(ctx, args.steps, args.warmup)
+                r = bench_entropy(ctx, max(args.steps, 100) if args.workload == "all" else args.steps, args.warmup)
             else:
                 r = bench_solve(ctx, key, args.steps, args.warmup)
         except SystemExit:

@@ -492,6 +492,16 @@ inline int zero_copy_max_batch()
   return v;
 }
 
+// EB_SOLVE_PDL=0 turns programmatic dependent launch of the per-step kernels off
+inline bool solve_pdl()
+{
+  static const bool v = [] {
+    const char* e = std::getenv("EB_SOLVE_PDL");
+    return !e || std::atoi(e) != 0;
+  }();
+  return v;
+}
+
 namespace
 {
 // num_basis 13..24 run solve_kernel2 (solve_kernel_v2.cuh); EB_SOLVE_V1=1 keeps the round-1 kernel for A/B timing
@@ -545,8 +555,21 @@ struct SolveLaunch
       configured[dev & 63] = bytes;
     }
     const int grid = (p.B + WARPS - 1) / WARPS;
-    kernel<<<grid, WARPS * 32, bytes, s>>>(p);
-    return cudaGetLastError();
+    // Programmatic dependent launch: consecutive control() steps on one stream are kernel -> kernel dependencies; the
+    // next step's CTAs may be placed while this step's last ones drain (every global access of the kernel sits behind
+    // its griddepcontrol.wait, so the data dependency is the stream's).  EB_SOLVE_PDL=0 turns it off.
+    static const bool pdl = solve_pdl();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)(WARPS * 32));
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
   }
   static cudaError_t launch(const eb::SolveParams& p, int rounds, cudaStream_t s)
   {
@@ -1560,8 +1583,19 @@ eb_status eb_control_dev_gather_wait(eb_controller* c, eb_peer_group* g, double 
   pp.need = need;
   pp.done_counter = g->counter;
   const int blocks = (int)std::max<long long>(1, std::min<long long>(64, (g->elems / 2 + 255) / 256));
-  eb::peer_publish_wait_kernel<<<blocks, 256, 0, c->stream>>>(pp);
-  EB_CUDA(cudaGetLastError());
+  {
+    // programmatic dependent launch behind the solve kernel (and ahead of the next step's): see SolveLaunch::launch_w
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = solve_pdl() ? 1 : 0;
+    EB_CUDA(cudaLaunchKernelEx(&cfg, eb::peer_publish_wait_kernel, pp));
+  }
   c->launches += 1;
   g->step += 1;
   return EB_OK;

@@ -79,6 +79,9 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(const PublishParams p
 // fences, raises this rank's flags on every peer and then waits for the peers' flags.
 __global__ void __launch_bounds__(256) peer_publish_wait_kernel(const PublishParams p)
 {
+  // programmatic dependent launch: the solve kernel ahead has completed (its rows are in p.src) past this point
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x < p.n_peer)
     while (*(const volatile unsigned long long*)(p.my_flags + threadIdx.x) < p.need) __nanosleep(100);
   __syncthreads();

@@ -60,7 +60,7 @@ constexpr int kTabStride = 20;   // 16 slots + 4 pad: 20 % 16 == 4 -> conflict-f
 
 #ifdef EB_PHASE_TIMING
 // debug build only: per-instance clock64() stamps at the phase boundaries
-constexpr int kPhaseSlots = 8;
+constexpr int kPhaseSlots = 16;
 __device__ long long g_phase[65536 * kPhaseSlots];
 #define EB_PHASE(idx)                                                                      \
   do                                                                                       \
@@ -180,6 +180,15 @@ __device__ __forceinline__ void publish_first_twist(const SolveParams& p, const 
       }
     }
   }
+}
+
+// Programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization): wait for the kernel ahead in the
+// stream to complete and flush, then let the kernel behind start placing its CTAs as this one's drain.  Both are no-ops
+// for a launch without the attribute.
+__device__ __forceinline__ void grid_dependency_wait()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 template <int MODEL>
@@ -382,6 +391,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
   const int nb = p.nb, K = nb * nb;
 
   const int inst = blockIdx.x * WARPS + warp;
+  grid_dependency_wait();  // programmatic dependent launch: nothing global is touched before the previous kernel is complete
   if (inst >= p.B) return;
 #if EB_ABL & 128
   if (lane < 3) p.u0[(size_t)inst * 3 + lane] = 0.0;  // ablation timing only: the launch itself
@@ -486,12 +496,13 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
       rec[7 * npad + i] = sb;
     }
     const int nvalid = min(32, p.N - r * 32);
+    if (r < 2) EB_PHASE(2 + 2 * r);
     coeff_chunk<NB>(tabx, lane, valid, nvalid, ca, cb, acc);
+    if (r < 2) EB_PHASE(3 + 2 * r);
   }
 
   // ---- c_k, S = lamda .* (c_k - phi_k) (:422), ergodic metric ---------------
   __syncwarp();
-  EB_PHASE(2);
   {
     const int g = lane >> 2, q = lane & 3;
     const double inv_t = 1.0 / (double)(p.M + p.N);  // basis.cpp:119
@@ -525,7 +536,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
     }
   }
   __syncwarp();
-  EB_PHASE(3);
+  EB_PHASE(6);
 
   // ---- per round, last round first: gradient of the ergodic metric, one time
   //      step per lane (:419-436), then the backward co-state pass and the
@@ -739,6 +750,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
     // dF/dx = -a sin(a x) cos(b y), dF/dy = -b cos(a x) sin(b y); times expl_weight (:433)
     ex = -ex * p.w;
     ey = -ey * p.w;
+    if (rounds - 1 - r < 2) EB_PHASE(7 + 2 * (rounds - 1 - r));
 #ifdef EB_DEBUG_DUMP
     if (inst == 0 && i < 4096)
     {
@@ -820,14 +832,15 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
     }
     if (valid && !finite) atomicOr(p.fault, 4);  // NaN / Inf guard
     if (r == 0) publish_first_twist(p, inst, lane, un);
+    if (rounds - 1 - r < 2) EB_PHASE(8 + 2 * (rounds - 1 - r));
   }
-  EB_PHASE(4);
+  EB_PHASE(11);
 #ifdef EB_PHASE_TIMING
   if (lane == 0 && inst < 65536)
   {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    g_phase[inst * kPhaseSlots + 6] = smid;
+    g_phase[inst * kPhaseSlots + 15] = smid;
   }
 #endif
 }

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? Solve2Cfg<N
   const int g = lane >> 2, q = lane & 3;
 
   const int inst = blockIdx.x * WARPS + warp;
+  grid_dependency_wait();  // programmatic dependent launch: see solve_kernel.cuh
   if (inst >= p.B) return;
 
   double* const tab = smem + warp * (Cfg::kTabDoubles + Cfg::kFields * npad);

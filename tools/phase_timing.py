@@ -13,11 +13,13 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-DBG = "/tmp/libergodic_b200_phase.so"
-csrc = os.path.join(ROOT, "ergodic_exploration_b200", "csrc")
-subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-                       "-Xcompiler", "-fPIC", "-DEB_PHASE_TIMING", "-shared", "-o", DBG,
-                       os.path.join(csrc, "ergodic_b200.cu"), "-lcudart"])
+DBG = os.path.join(ROOT, "variants", "lib_phase.so")  # tools/variants.sh phase "-DEB_PHASE_TIMING"
+if not os.path.exists(DBG):
+    csrc = os.path.join(ROOT, "ergodic_exploration_b200", "csrc")
+    os.makedirs(os.path.dirname(DBG), exist_ok=True)
+    subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-Xcompiler", "-fPIC", "-DEB_PHASE_TIMING", "-shared", "-o", DBG,
+                           os.path.join(csrc, "ergodic_b200.cu"), "-lcudart"])
 os.environ["EB_LIB_PATH"] = DBG
 
 import numpy as np  # noqa: E402
@@ -43,18 +45,21 @@ for _ in range(3):
     ctl.control(bench.BOUNDS, xd)
 torch.cuda.synchronize()
 lib = capi.load()
-buf = np.zeros((B, 8), dtype=np.int64)
+S = 16
+buf = np.zeros((B, S), dtype=np.int64)
 assert lib.eb_debug_phase_dump(buf.ctypes.data_as(C.c_void_p), B) == 0
-names = ["replay c_k", "rollout + c_k", "S / metric", "gradient + co-state"]
-sm = buf[:, 6]
-print(f"workload {name}: {B} instances; stamps are per-SM clocks, spans are per SM then averaged")
+names = ["replay c_k", "round 0: rollout + trig", "round 0: c_k tables + DMMA", "round 1: rollout + trig",
+         "round 1: c_k tables + DMMA", "S / metric", "last round: gradient", "last round: co-state + update",
+         "first round: gradient", "first round: co-state + update", "exit"]
+sm = buf[:, 15]
+print(f"workload {name}: {B} instances (solve_kernel v1 stamps; horizons of at most 2 rounds); cycles of the SM clock")
 spans = []
 for s in np.unique(sm):
     t = buf[sm == s]
-    spans.append((t[:, 4].max() - t[:, 0].min(), len(t)))
+    spans.append((t[:, 11].max() - t[:, 0].min(), len(t)))
 spans = np.array(spans)
 print(f"SM busy span: mean {spans[:, 0].mean():.0f} cycles, max {spans[:, 0].max():.0f}; warps per SM {spans[:, 1].mean():.1f}")
-tot = (buf[:, 4] - buf[:, 0]).mean()
+tot = (buf[:, 11] - buf[:, 0]).mean()
 for i, n in enumerate(names):
     d = buf[:, i + 1] - buf[:, i]
-    print(f"  {n:20s} mean {d.mean():9.0f} cycles  ({100 * d.mean() / tot:5.1f}% of a warp's {tot:.0f})  min {d.min()} max {d.max()}")
+    print(f"  {n:32s} mean {d.mean():9.0f} cycles  ({100 * d.mean() / tot:5.1f}% of a warp's {tot:.0f})  min {d.min()} max {d.max()}")
