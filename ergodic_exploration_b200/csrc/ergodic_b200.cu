@@ -109,6 +109,7 @@ struct eb_phik_plan
   double *d_T = nullptr;                    // stage-1 result [ny][32]
   double *d_parts = nullptr;                // partial 32x32 blocks
   double *d_phik = nullptr, *d_sum = nullptr;  // staging for the _host call
+  double* d_phi_stage = nullptr;               // device copy of the density for the _host call (kept between calls)
   unsigned int* d_done = nullptr;              // arrival counter of the TMA kernel's fused final sum
   const eb::PhikTmaPeer* peer = nullptr;       // set for the duration of eb_phik_execute_allreduce_dev
   int max_parts = 0;
@@ -297,6 +298,7 @@ void eb_phik_plan_destroy(eb_phik_plan* p)
   cudaFree(p->d_parts);
   cudaFree(p->d_phik);
   cudaFree(p->d_sum);
+  cudaFree(p->d_phi_stage);
   cudaFree(p->d_done);
   delete p;
 }
@@ -394,9 +396,9 @@ eb_status eb_phik_execute_host(eb_phik_plan* p, const double* phi, double* phik,
   EB_TRACE("eb_phik_execute_host");
   if (!p || !phi || !phik) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_execute_host: NULL argument");
   EB_CUDA(cudaSetDevice(p->device));
-  double* d_phi = nullptr;
   const size_t bytes = sizeof(double) * (size_t)p->nx * p->ny;
-  EB_CUDA(cudaMalloc(&d_phi, bytes));
+  if (!p->d_phi_stage) EB_CUDA(cudaMalloc(&p->d_phi_stage, bytes));  // once per plan: a map update reuses it
+  double* const d_phi = p->d_phi_stage;
   cudaError_t e = cudaMemcpyAsync(d_phi, phi, bytes, cudaMemcpyHostToDevice, p->stream);
   eb_status st = EB_OK;
   if (e == cudaSuccess) st = eb_phik_execute_dev(p, d_phi, p->d_phik, p->d_sum);
@@ -405,7 +407,6 @@ eb_status eb_phik_execute_host(eb_phik_plan* p, const double* phi, double* phik,
   if (e == cudaSuccess && st == EB_OK && phi_sum)
     e = cudaMemcpyAsync(phi_sum, p->d_sum, sizeof(double), cudaMemcpyDeviceToHost, p->stream);
   if (e == cudaSuccess && st == EB_OK) e = cudaStreamSynchronize(p->stream);
-  cudaFree(d_phi);
   if (st != EB_OK) return st;
   if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_phik_execute_host: ") + cudaGetErrorString(e));
   return EB_OK;
@@ -451,6 +452,7 @@ struct eb_controller
   long long hist_cap = 0, mem_count = 0;
   double *d_phik = nullptr, *d_lamk = nullptr;
   double *d_u0 = nullptr, *d_metric = nullptr, *d_ck = nullptr, *d_x = nullptr;
+  double* d_xt = nullptr;                  // [B][N][3] staging of eb_opt_traj_host (allocated on first use, kept)
   int *d_mem_idx_in = nullptr, *d_mem_idx_out = nullptr;
   int *h_fault = nullptr, *d_fault = nullptr;  // pinned + mapped: the kernels set it, the host reads it after a sync
   int last_idx_count = 0;
@@ -782,6 +784,7 @@ void eb_destroy(eb_controller* c)
   cudaFree(c->d_phik);
   cudaFree(c->d_lamk);
   cudaFree(c->d_u0);
+  cudaFree(c->d_xt);
   cudaFree(c->d_metric);
   cudaFree(c->d_ck);
   cudaFree(c->d_x);
@@ -1162,14 +1165,13 @@ eb_status eb_opt_traj_host(eb_controller* c, double* xt)
   if (!c || !xt) return fail(EB_ERR_INVALID_ARGUMENT, "eb_opt_traj_host: NULL argument");
   EB_CUDA(cudaSetDevice(c->cfg.device));
   const size_t bytes = sizeof(double) * 3 * (size_t)c->N * c->B;
-  double* d = nullptr;
-  EB_CUDA(cudaMalloc(&d, bytes));
+  if (!c->d_xt) EB_CUDA(cudaMalloc(&c->d_xt, bytes));  // optTraj() runs every tick (exploration.hpp:234): keep it
+  double* const d = c->d_xt;
   eb_status st = eb_opt_traj_dev(c, d);
   cudaError_t e = cudaSuccess;
   if (st == EB_OK) e = cudaMemcpyAsync(xt, d, bytes, cudaMemcpyDeviceToHost, c->stream);
   if (st == EB_OK && e == cudaSuccess) st = check_fault(c);
   cudaStreamSynchronize(c->stream);
-  cudaFree(d);
   if (st != EB_OK) return st;
   if (e != cudaSuccess) return fail(EB_ERR_CUDA, std::string("eb_opt_traj_host: ") + cudaGetErrorString(e));
   return EB_OK;
