@@ -295,7 +295,10 @@ class ErgodicControl:
     def control(self, grid, x, mem_idx=None, u0=None, metric=None):
         """One control() iteration for all instances.  Returns u0 (B, 3); pass
         ``metric`` (B,) to also receive sum_k lamda_k (c_k - phi_k)^2."""
-        b = grid.as_tuple() if hasattr(grid, "as_tuple") else tuple(float(v) for v in grid)
+        if type(grid) is tuple:  # a control loop passes the same bounds tuple every tick
+            b = grid
+        else:
+            b = grid.as_tuple() if hasattr(grid, "as_tuple") else tuple(float(v) for v in grid)
         if _is_cuda_tensor(x):
             self._sync_stream()  # device path: run on torch's current stream
             assert x.dtype == torch.float64 and x.is_contiguous() and x.numel() == 3 * self.batch
@@ -318,9 +321,10 @@ class ErgodicControl:
                 idx_p = mem_idx.ctypes.data
             met_p = self._host_ptr(metric) if metric is not None else None
             st = self._lib.eb_control_host(self._h, *b, self._host_ptr(x), idx_p, self._host_ptr(u0), met_p)
-        if st == capi.EB_ERR_INVALID_ARGUMENT:
-            raise ValueError(self._lib.eb_last_error().decode())
-        check(st)
+        if st != capi.EB_OK:
+            if st == capi.EB_ERR_INVALID_ARGUMENT:
+                raise ValueError(self._lib.eb_last_error().decode())
+            check(st)
         return u0
 
     def check(self) -> None:

@@ -587,7 +587,7 @@ struct SolveLaunch
       const char* e = std::getenv("EB_SOLVE_WIDE");
       return !e || std::atoi(e) != 0;
     }();
-    if (wide_ok && p.n_peer == 0 && p.B <= sms * kWide && p.B > sms * eb::kSolveWarps && smem(p.N, kWide) <= wide_limit())
+    if (wide_ok && p.n_peer == 0 && p.B <= sms * kWide && p.B > sms * eb::kSolveWarps && smem(p.N, kWide) + 2048 <= wide_limit())
       return launch_w<kWide>(p, s);
     return launch_w<eb::kSolveWarps>(p, s);
   }

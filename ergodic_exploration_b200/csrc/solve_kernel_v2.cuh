@@ -147,7 +147,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? Solve2Cfg<N
   const int g = lane >> 2, q = lane & 3;
 
   const int inst = blockIdx.x * WARPS + warp;
+  __shared__ WideIo<WARPS> wio;  // wide single-wave CTAs: poses in / first twists out as one segment (solve_kernel.cuh)
   grid_dependency_wait();  // programmatic dependent launch: see solve_kernel.cuh
+  if constexpr (WideIo<WARPS>::kOn) wide_io_load(wio, p);
   if (inst >= p.B) return;
 
   double* const tab = smem + warp * (Cfg::kTabDoubles + Cfg::kFields * npad);
@@ -206,7 +208,11 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? Solve2Cfg<N
   double* ut_out = p.ut_out + (size_t)inst * p.N * 3;
   RolloutCarry cy;
   {
-    const double xv = lane < 3 ? p.x[(size_t)inst * 3 + lane] : 0.0;
+    double xv = 0.0;
+    if constexpr (WideIo<WARPS>::kOn)
+      xv = lane < 3 ? wio.x[3 * warp + lane] : 0.0;
+    else
+      xv = lane < 3 ? p.x[(size_t)inst * 3 + lane] : 0.0;
     if (p.pose_out && lane < 3) p.pose_out[(size_t)inst * 3 + lane] = xv;
     cy.x = __shfl_sync(kFull, xv, 0);
     cy.y = __shfl_sync(kFull, xv, 1);
@@ -521,7 +527,13 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? Solve2Cfg<N
       if (valid) ut_out[i * 3 + c] = un[c];
     }
     if (valid && !finite) atomicOr(p.fault, 4);  // NaN / Inf guard
-    if (r == 0) publish_first_twist(p, inst, lane, un);
+    if (r == 0)
+    {
+      if constexpr (WideIo<WARPS>::kOn)
+        wide_io_store(wio, p, lane, warp, un);
+      else
+        publish_first_twist(p, inst, lane, un);
+    }
   }
 }
 }  // namespace eb
