@@ -398,13 +398,15 @@ class PhikPlan:
     configTarget grid (Target::fill normalisation + Basis::spatialCoeff)."""
 
     def __init__(self, nx: int, ny: int, resolution: float, lx: float, ly: float, nb: int, device: int = 0,
-                 algo: int = 0, row_begin: int = 0, ny_total: Optional[int] = None):
-        """ny rows starting at row_begin of an ny_total-row grid (default: the whole grid)"""
+                 algo: int = 0, row_begin: int = 0, ny_total: Optional[int] = None, x_first: float = 0.0,
+                 y_first: float = 0.0):
+        """ny rows starting at row_begin of an ny_total-row grid (default: the whole grid); x_first / y_first: the
+        coordinate of the first sample point (0: the configTarget grid; resolution / 2: cell centres)"""
         self._lib = capi.load()
         h = C.c_void_p()
         ny_total = ny if ny_total is None else ny_total
-        st = self._lib.eb_phik_plan_create_rows(device, nx, ny_total, row_begin, ny, float(resolution), float(lx),
-                                                float(ly), nb, C.byref(h))
+        st = self._lib.eb_phik_plan_create_ex(device, nx, ny_total, row_begin, ny, float(resolution), float(lx),
+                                              float(ly), nb, float(x_first), float(y_first), C.byref(h))
         if st == capi.EB_ERR_INVALID_ARGUMENT:
             raise ValueError(self._lib.eb_last_error().decode())
         check(st)

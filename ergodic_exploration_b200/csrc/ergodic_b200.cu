@@ -2333,11 +2333,16 @@ struct eb_map_target
   cudaStream_t stream = nullptr;
   eb_phik_plan* plan = nullptr;
   double* d_lut = nullptr;       // entropy of the 256 int8 patterns
-  double* d_phi = nullptr;       // un-normalised density [ysize][xsize]
+  double* d_phi = nullptr;       // un-normalised density [ysize][xsize]: written by the two-kernel route or on demand
+  const signed char* last_cells = nullptr;  // device cells of the last execute (must stay alive for a later density request)
+  bool density_valid = false;    // d_phi holds the density of last_cells
   signed char* d_cells = nullptr;  // staging for the _host call
   double *d_phik = nullptr, *d_sum = nullptr;
   long long launches = 0;
 };
+extern "C" {
+static eb_status map_density(eb_map_target* m);
+}
 
 extern "C" {
 
@@ -2366,9 +2371,7 @@ eb_status eb_map_target_create(int device, unsigned int xsize, unsigned int ysiz
     delete m;
     return st;
   }
-  const size_t cells = (size_t)xsize * ysize;
   cudaError_t e = cudaMalloc(&m->d_lut, sizeof(double) * 256);
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_phi, sizeof(double) * cells);
   if (e == cudaSuccess) e = cudaMalloc(&m->d_phik, sizeof(double) * 1024);
   if (e == cudaSuccess) e = cudaMalloc(&m->d_sum, sizeof(double));
   if (e == cudaSuccess)
@@ -2409,7 +2412,12 @@ eb_status eb_map_target_set_stream(eb_map_target* m, void* s)
 }
 
 long long eb_map_target_launch_count(const eb_map_target* m) { return m ? m->launches + m->plan->launches : 0; }
-double* eb_map_target_density_dev(eb_map_target* m) { return m ? m->d_phi : nullptr; }
+double* eb_map_target_density_dev(eb_map_target* m)
+{
+  // the fused execute never writes the density: materialise it from the last execute's cells on demand
+  if (!m || cudaSetDevice(m->device) != cudaSuccess || map_density(m) != EB_OK) return nullptr;
+  return m->d_phi;
+}
 
 eb_status eb_map_target_extent(const eb_map_target* m, double* lx, double* ly)
 {
@@ -2419,18 +2427,55 @@ eb_status eb_map_target_extent(const eb_map_target* m, double* lx, double* ly)
   return EB_OK;
 }
 
+static bool map_fused_enabled()
+{
+  static const bool v = [] {
+    const char* e = std::getenv("EB_MAP_FUSED");
+    return !e || std::atoi(e) != 0;
+  }();
+  return v;
+}
+
+// the density of the last execute's cells, materialised (allocated on first use)
+static eb_status map_density(eb_map_target* m)
+{
+  if (m->density_valid) return EB_OK;
+  if (!m->last_cells) return fail(EB_ERR_INVALID_ARGUMENT, "map target: no execute yet");
+  const long long cells = (long long)m->xsize * m->ysize;
+  if (!m->d_phi) EB_CUDA(cudaMalloc(&m->d_phi, sizeof(double) * (size_t)cells));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  const int grid = (int)std::min<long long>((cells / 512 + 7) / 8 + 1, (long long)sms * 8);  // 8 warps per CTA, 512 cells per warp iteration
+  eb::entropy_density_kernel<<<grid, 256, 0, m->stream>>>(m->last_cells, cells, m->d_lut, m->d_phi);
+  m->launches += 1;
+  EB_CUDA(cudaGetLastError());
+  m->density_valid = true;
+  return EB_OK;
+}
+
 eb_status eb_map_target_execute_dev(eb_map_target* m, const signed char* cells_dev, double* phik_dev, double* phi_sum_dev)
 {
   EB_TRACE("eb_map_target_execute_dev");
   if (!m || !cells_dev || !phik_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_map_target_execute_dev: NULL argument");
   EB_CUDA(cudaSetDevice(m->device));
-  const long long cells = (long long)m->xsize * m->ysize;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
-  const int grid = (int)std::min<long long>((cells / 512 + 7) / 8 + 1, (long long)sms * 8);  // 8 warps per CTA, 512 cells per warp iteration
-  eb::entropy_density_kernel<<<grid, 256, 0, m->stream>>>(cells_dev, cells, m->d_lut, m->d_phi);
-  m->launches += 1;
-  EB_CUDA(cudaGetLastError());
+  m->last_cells = cells_dev;
+  m->density_valid = false;
+  // ONE kernel when the folded TMA tile kernel applies: the bytes are staged by TMA and the entropy table is looked up in
+  // shared memory -- the 8 B / cell density is never written (EB_MAP_FUSED=0: always the two-kernel route)
+  eb_phik_plan* const pl = m->plan;
+  const bool big = (long long)pl->nx * pl->ny >= (1 << 18);  // as phik_execute: small grids take the simple kernels
+  if (map_fused_enabled() && pl->fold && pl->d_cxtf && (pl->algo == 4 || (pl->algo == 0 && big)) && !pl->peer &&
+      eb::phik_tma_u8_supported(pl->nx, pl->ny) && eb::phik_tma_encoder() && (reinterpret_cast<uintptr_t>(cells_dev) & 15) == 0)
+  {
+    const eb::PhikTmaOut out{ pl->d_done, pl->nb, phik_dev, phi_sum_dev, nullptr, nullptr };
+    const int nparts = eb::phik_tma_launch_u8(cells_dev, m->d_lut, pl->nx, pl->ny, pl->d_cxtf, pl->d_cy, pl->d_parts,
+                                              pl->max_parts, out, m->stream);
+    if (nparts < 0) return fail(EB_ERR_CUDA, std::string("phik_tma_launch_u8: ") + cudaGetErrorString(cudaGetLastError()));
+    m->launches += 1;
+    return EB_OK;
+  }
+  const eb_status st = map_density(m);
+  if (st != EB_OK) return st;
   return eb_phik_execute_dev(m->plan, m->d_phi, phik_dev, phi_sum_dev);
 }
 

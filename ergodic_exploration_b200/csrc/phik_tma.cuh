@@ -34,20 +34,28 @@ constexpr int kPtThreads = (kPtWarps + 1) * 32;
 constexpr int kPtBoxBytes = kPtRows * kPtBox * 8;  // 8 KB
 constexpr int kPtTPitch = 33;
 
-template <bool FOLD>
+// U8: the density is a byte -> double table lookup of an occupancy grid (map_target.cuh); the stage then holds the
+// BYTES of the 64 x 32 left cells and of their 64 x 32 mirrors (two boxes of 2 KB, no swizzle) and the consumers look
+// the values up in a 256-entry table in shared memory -- the 8 B / cell density never exists in HBM.
+constexpr int kPtU8BoxBytes = kPtRows * 32;  // 64 rows x 32 one-byte cells
+
+template <bool FOLD, bool U8 = false>
 struct PtGeom
 {
+  static_assert(!U8 || FOLD, "the byte-source kernel is the folded one");
   static constexpr int kCols = FOLD ? 32 : 64;             // contraction columns (pairs with the fold) per stage
   static constexpr int kBoxes = 4;                         // FOLD: 2 left + 2 mirrored; else 4 consecutive
-  static constexpr int kPhiBytes = kBoxes * kPtBoxBytes;   // 32 KB
+  static constexpr int kPhiBytes = U8 ? 2 * kPtU8BoxBytes : kBoxes * kPtBoxBytes;  // 4 KB | 32 KB
   static constexpr int kCxBytes = kCols * kPdPitch * 8;    // 9 / 18 KB
   static constexpr int kStageBytes = kPhiBytes + ((kCxBytes + 1023) / 1024) * 1024;
 #ifndef EB_PT_STAGES_FOLD
 #define EB_PT_STAGES_FOLD 4
 #endif
-  static constexpr int kStages = FOLD ? EB_PT_STAGES_FOLD : 3;
+  static constexpr int kStages = U8 ? 6 : (FOLD ? EB_PT_STAGES_FOLD : 3);
   static constexpr int kKSteps = kCols / 16;               // k-steps per warp and stage (a quarter of the columns, 4 per step)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kPtRows * kPtTPitch * 8 + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int kLutBytes = U8 ? 256 * 8 : 0;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kPtRows * kPtTPitch * 8 + 256 + kLutBytes + 1024;  // + barriers + table + alignment slack
 };
 
 inline bool phik_tma_supported(int nx, int ny) { return nx % 2 == 0 && nx >= 64 && ny >= 1; }
@@ -109,6 +117,7 @@ struct PhikTmaParams
   const double* my_recv;                       // this rank's receive buffer of this step's parity, [n_peer][1024]
   unsigned long long step;                     // 1-based step number = flag value
   unsigned long long* trace;                   // EB_PT_TRACE builds: [gridDim.x][8] globaltimer stamps, else null
+  const double* lut;                           // U8 kernels: density value of every byte, [256]
 };
 
 #ifdef EB_PT_TRACE
@@ -126,17 +135,18 @@ __device__ __forceinline__ void pt_stamp(const PhikTmaParams& p, int slot)
 #define PT_STAMP(slot)
 #endif
 
-template <bool FOLD>
+template <bool FOLD, bool U8 = false>
 __global__ void __launch_bounds__(kPtThreads, 1)
     phik_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PhikTmaParams p)
 {
-  using G = PtGeom<FOLD>;
+  using G = PtGeom<FOLD, U8>;
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B destinations must be 1024-byte aligned
   unsigned char* const base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   double* const tstage = reinterpret_cast<double*>(base + G::kStages * G::kStageBytes);  // [64][33]
   uint64_t* const full = reinterpret_cast<uint64_t*>(base + G::kStages * G::kStageBytes + kPtRows * kPtTPitch * 8);
   uint64_t* const empty = full + G::kStages;
+  double* const lut = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(full) + 256);  // U8 only
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   PT_STAMP(0);
@@ -169,7 +179,13 @@ __global__ void __launch_bounds__(kPtThreads, 1)
         unsigned char* const st = base + s * G::kStageBytes;
         mbar_expect_tx(&full[s], G::kPhiBytes + G::kCxBytes);
         const int row0 = band * kPtRows, col0 = k * G::kCols;
-        if (FOLD)
+        if (U8)
+        {
+          // cells col0 .. col0 + 31 and their mirrors nx - col0 - 32 .. nx - col0 - 1 (ascending: pair p <-> byte 31 - p)
+          tma_tile_g2s(st, &tmap, col0, row0, &full[s]);
+          tma_tile_g2s(st + kPtU8BoxBytes, &tmap, p.nx - col0 - 32, row0, &full[s]);
+        }
+        else if (FOLD)
         {
           // pairs col0 .. col0 + 31: left columns ascending, and their mirrors nx-1-c as two ascending boxes
           tma_tile_g2s(st + 0 * kPtBoxBytes, &tmap, col0, row0, &full[s]);
@@ -198,6 +214,13 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   const int rb = warp & 3, cq = warp >> 2;  // 16-row block, column quarter
   const int rho = (g >> 1) | ((g & 1) << 2);  // box row (within a group of 8) that feeds DMMA row g
 
+  if (U8)
+  {
+    if (threadIdx.x < 256) lut[threadIdx.x] = __ldg(p.lut + threadIdx.x);
+    pt_consumer_barrier();
+  }
+
+  const bool hi_orders = p.nb > 16;  // orders 16 .. 31 (order tiles 1, 3 with the fold; 2, 3 without) are wanted
   double P[2] = { 0.0, 0.0 };  // this warp's 8x8 tile of the CTA's 32x32 partial
   double T[2][4][2];           // [row group][order tile][2]
 #pragma unroll
@@ -226,8 +249,21 @@ __global__ void __launch_bounds__(kPtThreads, 1)
       for (int r = 0; r < 2; r++)
       {
         const int row = 16 * rb + 8 * r + rho;
-        const double2 lo = *reinterpret_cast<const double2*>(st + bx * kPtBoxBytes + row * 128 + ((ch ^ rho) << 4));
-        const double2 hi = *reinterpret_cast<const double2*>(st + (2 + bx) * kPtBoxBytes + row * 128 + (((7 - ch) ^ rho) << 4));
+        double2 lo, hi;
+        if (U8)
+        {
+          // pairs 8 cq + 2 q, + 1: two bytes of the left box; their mirrors are bytes 31 - p of the mirror box
+          const int p0 = 8 * cq + 2 * q;
+          const unsigned int wl = *reinterpret_cast<const unsigned short*>(st + row * 32 + p0);
+          const unsigned int wh = *reinterpret_cast<const unsigned short*>(st + kPtU8BoxBytes + row * 32 + 30 - p0);
+          lo = make_double2(lut[wl & 255u], lut[wl >> 8]);
+          hi = make_double2(lut[wh & 255u], lut[wh >> 8]);
+        }
+        else
+        {
+          lo = *reinterpret_cast<const double2*>(st + bx * kPtBoxBytes + row * 128 + ((ch ^ rho) << 4));
+          hi = *reinterpret_cast<const double2*>(st + (2 + bx) * kPtBoxBytes + row * 128 + (((7 - ch) ^ rho) << 4));
+        }
         ev[r][0] = lo.x + hi.y;
         od[r][0] = lo.x - hi.y;
         ev[r][1] = lo.y + hi.x;
@@ -237,14 +273,22 @@ __global__ void __launch_bounds__(kPtThreads, 1)
       for (int ks = 0; ks < 2; ks++)
       {
         const double* brow = cxs + (8 * cq + 4 * ks + q) * kPdPitch + g;
-        const double b0 = brow[0], b1 = brow[8], b2 = brow[16], b3 = brow[24];
+        const double b0 = brow[0], b2 = brow[16];
 #pragma unroll
         for (int r = 0; r < 2; r++)
         {
           dmma884(T[r][0][0], T[r][0][1], ev[r][ks], b0);  // orders 0, 2, .., 14
-          dmma884(T[r][1][0], T[r][1][1], ev[r][ks], b1);  // orders 16, .., 30
           dmma884(T[r][2][0], T[r][2][1], od[r][ks], b2);  // orders 1, 3, .., 15
-          dmma884(T[r][3][0], T[r][3][1], od[r][ks], b3);  // orders 17, .., 31
+        }
+        if (hi_orders)  // nb <= 16 never reads orders 16 .. 31: half the DMMAs
+        {
+          const double b1 = brow[8], b3 = brow[24];
+#pragma unroll
+          for (int r = 0; r < 2; r++)
+          {
+            dmma884(T[r][1][0], T[r][1][1], ev[r][ks], b1);  // orders 16, .., 30
+            dmma884(T[r][3][0], T[r][3][1], od[r][ks], b3);  // orders 17, .., 31
+          }
         }
       }
     }
@@ -267,14 +311,22 @@ __global__ void __launch_bounds__(kPtThreads, 1)
       for (int ks = 0; ks < 4; ks++)
       {
         const double* brow = cxs + (16 * cq + 4 * ks + q) * kPdPitch + g;
-        const double b0 = brow[0], b1 = brow[8], b2 = brow[16], b3 = brow[24];
+        const double b0 = brow[0], b1 = brow[8];
 #pragma unroll
         for (int r = 0; r < 2; r++)
         {
           dmma884(T[r][0][0], T[r][0][1], av[r][ks], b0);
           dmma884(T[r][1][0], T[r][1][1], av[r][ks], b1);
-          dmma884(T[r][2][0], T[r][2][1], av[r][ks], b2);
-          dmma884(T[r][3][0], T[r][3][1], av[r][ks], b3);
+        }
+        if (hi_orders)
+        {
+          const double b2 = brow[16], b3 = brow[24];
+#pragma unroll
+          for (int r = 0; r < 2; r++)
+          {
+            dmma884(T[r][2][0], T[r][2][1], av[r][ks], b2);
+            dmma884(T[r][3][0], T[r][3][1], av[r][ks], b3);
+          }
         }
       }
     }
@@ -485,6 +537,23 @@ inline bool phik_tma_make_map(const double* phi, int nx, int ny, CUtensorMap* ma
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// tensor map of a row-major [ny][nx] occupancy grid (one byte per cell): boxes of 64 rows x 32 cells, no swizzle, zero
+// fill outside (rows past the grid carry zero C_y weight, columns past nx / 2 zero C_x rows: whatever the table holds
+// for byte 0 never reaches the result)
+inline bool phik_tma_u8_supported(int nx, int ny) { return nx % 16 == 0 && nx >= 64 && ny >= 1; }
+inline bool phik_tma_make_map_u8(const signed char* cells, int nx, int ny, CUtensorMap* map)
+{
+  PFN_eb_encodeTiled enc = phik_tma_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = { (cuuint64_t)nx, (cuuint64_t)ny };
+  const cuuint64_t strides[1] = { (cuuint64_t)nx };
+  const cuuint32_t box[2] = { 32u, (cuuint32_t)kPtRows };
+  const cuuint32_t estr[2] = { 1, 1 };
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<signed char*>(cells), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Launches one persistent CTA per SM (fewer when there is less work than that); returns the number of partial
 // blocks written (= grid size) or -1 on failure (no encoder, misaligned density, launch error).
 struct PhikTmaPeer
@@ -505,15 +574,18 @@ struct PhikTmaOut
   const PhikTmaPeer* peer = nullptr;
 };
 
-template <bool FOLD>
-inline int phik_tma_launch_t(const double* phi, int nx, int ny, const double* cxp, const double* cy, double* parts,
-                             int max_parts, const PhikTmaOut& out, cudaStream_t stream)
+template <bool FOLD, bool U8 = false>
+inline int phik_tma_launch_t(const void* src, const double* lut, int nx, int ny, const double* cxp, const double* cy,
+                             double* parts, int max_parts, const PhikTmaOut& out, cudaStream_t stream)
 {
-  using G = PtGeom<FOLD>;
-  if ((reinterpret_cast<uintptr_t>(phi) & 15) != 0) return -1;
+  using G = PtGeom<FOLD, U8>;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) return -1;
   CUtensorMap map;
-  if (!phik_tma_make_map(phi, nx, ny, &map)) return -1;
+  if (U8 ? !phik_tma_make_map_u8(static_cast<const signed char*>(src), nx, ny, &map) :
+           !phik_tma_make_map(static_cast<const double*>(src), nx, ny, &map))
+    return -1;
   PhikTmaParams p{};
+  p.lut = lut;
   p.cxp = cxp;
   p.cy = cy;
   p.parts = parts;
@@ -547,7 +619,8 @@ inline int phik_tma_launch_t(const double* phi, int nx, int ny, const double* cx
   cudaGetDevice(&dev);
   if (!configured[dev & 63])
   {
-    if (cudaFuncSetAttribute(phik_tma_kernel<FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(phik_tma_kernel<FOLD, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes) !=
+        cudaSuccess)
       return -1;
     configured[dev & 63] = true;
   }
@@ -558,7 +631,7 @@ inline int phik_tma_launch_t(const double* phi, int nx, int ny, const double* cx
   cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * 8 * 1024, stream);
   p.trace = d_trace;
 #endif
-  phik_tma_kernel<FOLD><<<grid, kPtThreads, G::kSmemBytes, stream>>>(map, p);
+  phik_tma_kernel<FOLD, U8><<<grid, kPtThreads, G::kSmemBytes, stream>>>(map, p);
   if (cudaGetLastError() != cudaSuccess) return -1;
 #ifdef EB_PT_TRACE
   {
@@ -590,8 +663,15 @@ inline int phik_tma_launch_t(const double* phi, int nx, int ny, const double* cx
 inline int phik_tma_launch(const double* phi, int nx, int ny, const double* cxp, const double* cy, double* parts,
                            int max_parts, bool fold, const PhikTmaOut& out, cudaStream_t stream)
 {
-  return fold ? phik_tma_launch_t<true>(phi, nx, ny, cxp, cy, parts, max_parts, out, stream) :
-                phik_tma_launch_t<false>(phi, nx, ny, cxp, cy, parts, max_parts, out, stream);
+  return fold ? phik_tma_launch_t<true>(phi, nullptr, nx, ny, cxp, cy, parts, max_parts, out, stream) :
+                phik_tma_launch_t<false>(phi, nullptr, nx, ny, cxp, cy, parts, max_parts, out, stream);
+}
+
+// the folded kernel over an occupancy grid: density = lut[cell byte], looked up in shared memory (map_target.cuh)
+inline int phik_tma_launch_u8(const signed char* cells, const double* lut, int nx, int ny, const double* cxpf, const double* cy,
+                              double* parts, int max_parts, const PhikTmaOut& out, cudaStream_t stream)
+{
+  return phik_tma_launch_t<true, true>(cells, lut, nx, ny, cxpf, cy, parts, max_parts, out, stream);
 }
 
 // rows of the permuted C_x table the kernel may touch (the last chunk is padded to the stage width)

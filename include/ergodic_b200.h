@@ -346,7 +346,10 @@ eb_status eb_phik_execute_allreduce_dev(eb_phik_plan *p, eb_phik_peer *g, const 
  * Density from an occupancy grid: Phi[i][j] = entropy(cell / 100) (numerics.hpp:164-179 over GridMap::getCell,
  * grid.cpp:177-184; -1 = unknown), sampled at the cell centres of the map frame [0, xsize * res] x [0, ysize * res],
  * normalised like Target::fill (target.cpp:87) and contracted like Basis::spatialCoeff (basis.cpp:122-133).
- * One execute per map update; phik_dev can be handed to eb_set_phik_dev without a host round trip. */
+ * One execute per map update; phik_dev can be handed to eb_set_phik_dev without a host round trip.
+ * Large maps whose width is a multiple of 16 cells run as ONE kernel (the bytes are staged by TMA, the entropy table
+ * is looked up in shared memory, folded DMMA tiles): the density itself is then never written;
+ * eb_map_target_density_dev materialises it on demand from the cells of the last execute (which must still be alive). */
 typedef struct eb_map_target eb_map_target;
 eb_status eb_map_target_create(int device, unsigned int xsize, unsigned int ysize, double resolution, int nb,
                                eb_map_target **out);
@@ -355,7 +358,7 @@ eb_status eb_map_target_set_stream(eb_map_target *m, void *cuda_stream);
 eb_status eb_map_target_execute_dev(eb_map_target *m, const signed char *cells_dev, double *phik_dev,
                                     double *phi_sum_dev /* may be NULL */);
 eb_status eb_map_target_execute_host(eb_map_target *m, const signed char *cells, double *phik, double *phi_sum);
-double *eb_map_target_density_dev(eb_map_target *m); /* un-normalised entropy density of the last execute, [ysize][xsize] */
+double *eb_map_target_density_dev(eb_map_target *m); /* un-normalised entropy density of the last execute, [ysize][xsize]; NULL on failure */
 eb_status eb_map_target_extent(const eb_map_target *m, double *lx, double *ly);
 long long eb_map_target_launch_count(const eb_map_target *m);
 /* phik_ <- a device buffer of K doubles (stream-ordered copy), basis extent (lx, ly) */

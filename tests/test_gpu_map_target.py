@@ -43,10 +43,14 @@ def test_entropy_density_matches_reference_golden():
     assert abs(mt.last_sum - G["entropy"].sum()) <= 1e-9 * G["entropy"].sum()
 
 
-@pytest.mark.parametrize("nx,ny,nb", [(512, 512, 16), (1000, 600, 10), (333, 257, 12)])
+@pytest.mark.parametrize("nx,ny,nb", [(512, 512, 16), (1024, 1000, 20), (2048, 130, 32), (4096, 64, 8), (1000, 600, 10),
+                                      (333, 257, 12)])
 def test_map_target_shapes(nx, ny, nb):
-    """large grids go through the folded TMA tile kernel (cell centres are mirror-symmetric), odd widths through the
-    simple pair; compared with the oracle's entropy + spatialCoeff on a sub-sampled check of the coefficients"""
+    """large grids whose width is a multiple of 16 go through the FUSED kernel (TMA-staged bytes, entropy table in shared
+    memory, folded DMMA tiles: the density is never written), other large grids through entropy kernel + folded TMA tile
+    kernel, odd widths through the simple pair; compared with the oracle's entropy + spatialCoeff"""
+    import torch
+
     import ergodic_exploration_b200 as eb
 
     rng = np.random.default_rng(nx + ny)
@@ -56,6 +60,19 @@ def test_map_target_shapes(nx, ny, nb):
     dens = Oracle.entropy_grid(cells)
     want = centre_phik(dens, 0.05, nb)
     assert_coeff_close(got, want, f"map target {nx}x{ny} nb={nb}")
+    # the density is materialised on demand from the last execute's cells
+    assert_abs_rel_close(mt.density().cpu().numpy(), dens, "density on demand")
+    # a second map update through the device path: new cells, same object; one launch when fused
+    cells2 = np.where(rng.random((ny, nx)) < 0.7, 0, cells).astype(np.int8)
+    l0 = mt.launch_count()
+    got2 = mt.execute(torch.from_numpy(cells2).cuda()).cpu().numpy()
+    fused = nx % 16 == 0 and nx * ny >= (1 << 18)
+    assert mt.launch_count() - l0 == (1 if fused else (2 if nx * ny >= (1 << 18) and nx % 2 == 0 else 4))
+    assert_coeff_close(got2, centre_phik(Oracle.entropy_grid(cells2), 0.05, nb), "second update")
+    # the plain two-step route on the same density agrees to rounding
+    plan = eb.PhikPlan(nx, ny, 0.05, mt.lx, mt.ly, nb, x_first=0.025, y_first=0.025)
+    two_step = plan.execute(torch.from_numpy(Oracle.entropy_grid(cells2)).cuda()).cpu().numpy()
+    assert_coeff_close(got2, two_step, "fused vs density + phi_k")
 
 
 def test_controller_takes_the_map_target_without_host_round_trip():
