@@ -415,11 +415,14 @@ def bench_solve(ctx, key, steps, warmup, with_cpu=True):
         step_dev(i)
     for c_ in ctls:
         c_.check()
-    ctx.flush_l2()
+    if n_rot == 1:
+        ctx.flush_l2()  # one batch larger than L2; with rotating batches the rotation itself has evicted batch 0's state
     ctx.barrier()
     launches0 = launch_total()
     ea, eb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ctx.clocks.region(key):
+        # the host enqueues ahead of the device (a step costs ~11 us of host time): no launch bubble inside the pair
+        torch.cuda._sleep(int(min(steps, 400) * 15e-6 * 1.9e9))
         ea.record()
         for i in range(steps):
             step_dev(i)
