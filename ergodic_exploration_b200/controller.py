@@ -443,13 +443,15 @@ class PhikPlan:
         return out
 
     def execute_raw(self, phi, raw=None):
-        """un-normalised contraction of this plan's rows: (32, 32) torch tensor, raw[0, 0] = sum(phi)"""
+        """un-normalised contraction of this plan's rows: (ld, ld) torch tensor with ld = 32 for nb <= 32, else nb
+        rounded up to a multiple of 32; raw[0, 0] = sum(phi)"""
         s = torch.cuda.current_stream(self.device).cuda_stream
         check(self._lib.eb_phik_plan_set_stream(self._h, C.c_void_p(s)))
         assert _is_cuda_tensor(phi) and phi.dtype == torch.float64 and phi.is_contiguous()
         assert phi.numel() == self.nx * self.ny
         if raw is None:
-            raw = torch.empty((32, 32), dtype=torch.float64, device=phi.device)
+            ld = 32 if self.nb <= 32 else (self.nb + 31) // 32 * 32
+            raw = torch.empty((ld, ld), dtype=torch.float64, device=phi.device)
         check(self._lib.eb_phik_execute_raw_dev(self._h, C.c_void_p(phi.data_ptr()), C.c_void_p(raw.data_ptr())))
         return raw
 

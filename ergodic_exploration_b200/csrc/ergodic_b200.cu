@@ -30,6 +30,7 @@
 #include "phik_tma.cuh"
 #include "solve_kernel.cuh"
 #include "solve_kernel_v2.cuh"
+#include "solve_kernel_big.cuh"
 
 namespace
 {
@@ -97,6 +98,7 @@ struct eb_phik_plan
 {
   int device = 0, nx = 0, ny = 0, nb = 0, algo = 0;  // ny = rows held by this plan
   int ny_total = 0, row_begin = 0;
+  int ld = 32;  // leading dimension of the cosine tables, T and the raw block: 32, or nb rounded up to 32 (nb > 32)
   double resolution = 0, lx = 0, ly = 0;
   cudaStream_t stream = nullptr;
   double *d_xs = nullptr, *d_ys = nullptr;  // grid coordinates
@@ -179,8 +181,8 @@ eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin
   EB_TRACE("eb_phik_plan_create");
   if (!out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create: out is NULL");
   *out = nullptr;
-  if (nx < 1 || ny < 1 || nb < 1 || nb > 32)
-    return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create: need nx, ny >= 1 and 1 <= nb <= 32");
+  if (nx < 1 || ny < 1 || nb < 1 || nb > EB_MAX_NUM_BASIS)
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create: need nx, ny >= 1 and 1 <= nb <= " + std::to_string(EB_MAX_NUM_BASIS));
   if (row_begin < 0 || row_begin + ny > ny_total)
     return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_plan_create_rows: row range outside the grid");
   if (!(lx > 0.0) || !(ly > 0.0) || !(resolution > 0.0))
@@ -216,22 +218,26 @@ eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin
   } while (0)
   EB_CUDA_P(cudaMalloc(&p->d_xs, sizeof(double) * nx));
   EB_CUDA_P(cudaMalloc(&p->d_ys, sizeof(double) * ny));
-  EB_CUDA_P(cudaMalloc(&p->d_cx, sizeof(double) * (size_t)nx * eb::kPhikLd));
-  EB_CUDA_P(cudaMalloc(&p->d_cy, sizeof(double) * (size_t)ny * eb::kPhikLd));
-  EB_CUDA_P(cudaMalloc(&p->d_T, sizeof(double) * (size_t)ny * eb::kPhikLd));
-  // per-CTA blocks + the per-group sums of the TMA kernel's two-level final sum
-  EB_CUDA_P(cudaMalloc(&p->d_parts, sizeof(double) * 1024 * (size_t)(p->max_parts + eb::kPtMaxGroups)));
-  EB_CUDA_P(cudaMalloc(&p->d_phik, sizeof(double) * 1024));
+  const int ld = eb::phik_ld(nb);  // 32, or nb rounded up to 32 for the wide (nb > 32) route
+  const bool wide = nb > 32;       // simple pair only: the tile kernels are built around 32 x 32 coefficient blocks
+  p->ld = ld;
+  EB_CUDA_P(cudaMalloc(&p->d_cx, sizeof(double) * (size_t)nx * ld));
+  EB_CUDA_P(cudaMalloc(&p->d_cy, sizeof(double) * (size_t)ny * ld));
+  EB_CUDA_P(cudaMalloc(&p->d_T, sizeof(double) * (size_t)ny * ld));
+  // per-CTA blocks + the per-group sums of the TMA kernel's two-level final sum (wide: the one ld x ld raw block)
+  EB_CUDA_P(cudaMalloc(&p->d_parts, wide ? sizeof(double) * (size_t)ld * ld :
+                                           sizeof(double) * 1024 * (size_t)(p->max_parts + eb::kPtMaxGroups)));
+  EB_CUDA_P(cudaMalloc(&p->d_phik, sizeof(double) * (size_t)std::max(1024, nb * nb)));
   EB_CUDA_P(cudaMalloc(&p->d_sum, sizeof(double)));
   EB_CUDA_P(cudaMalloc(&p->d_done, sizeof(unsigned int) * (1 + eb::kPtMaxGroups)));
   EB_CUDA_P(cudaMemset(p->d_done, 0, sizeof(unsigned int) * (1 + eb::kPtMaxGroups)));
   EB_CUDA_P(cudaMemcpy(p->d_xs, xs.data(), sizeof(double) * nx, cudaMemcpyHostToDevice));
   EB_CUDA_P(cudaMemcpy(p->d_ys, ys.data(), sizeof(double) * ny, cudaMemcpyHostToDevice));
   // basis.cpp:85: cos(k * (PI / l) * x)
-  eb::cos_table_kernel<<<(nx * eb::kPhikLd + 255) / 256, 256>>>(p->d_xs, nx, eb::kPi / lx, nb, p->d_cx);
-  eb::cos_table_kernel<<<(ny * eb::kPhikLd + 255) / 256, 256>>>(p->d_ys, ny, eb::kPi / ly, nb, p->d_cy);
+  eb::cos_table_kernel<<<(unsigned)(((size_t)nx * ld + 255) / 256), 256>>>(p->d_xs, nx, eb::kPi / lx, nb, ld, p->d_cx);
+  eb::cos_table_kernel<<<(unsigned)(((size_t)ny * ld + 255) / 256), 256>>>(p->d_ys, ny, eb::kPi / ly, nb, ld, p->d_cy);
   p->launches += 2;
-  if (eb::phik_dmma_supported(nx, ny))
+  if (!wide && eb::phik_dmma_supported(nx, ny))
   {
     // room for the last column span's padding chunks (span <= nchunks)
     const int rows_padded = 2 * ((nx + eb::kPdChunk - 1) / eb::kPdChunk) * eb::kPdChunk;
@@ -261,7 +267,7 @@ eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin
       }
     }
   }
-  if (eb::phik_tma_supported(nx, ny))
+  if (!wide && eb::phik_tma_supported(nx, ny))
   {
     const int rows_u = eb::phik_tma_cx_rows(nx, false);
     EB_CUDA_P(cudaMalloc(&p->d_cxt, sizeof(double) * (size_t)rows_u * eb::kPdPitch));
@@ -316,6 +322,8 @@ eb_status eb_phik_plan_set_algo(eb_phik_plan* p, int algo)
   if (algo < 0 || algo > 5)
     return fail(EB_ERR_INVALID_ARGUMENT, "algo must be 0 (auto), 1 (simple), 2 / 3 (register-streamed DMMA tiles, with / without "
                                          "the mirror fold) or 4 / 5 (TMA-staged DMMA tiles, with / without the mirror fold)");
+  if (algo >= 2 && p->nb > 32)
+    return fail(EB_ERR_UNSUPPORTED, "the DMMA tile kernels contract 32 x 32 coefficient blocks: num_basis > 32 runs the simple pair (algo 0 / 1)");
   if ((algo == 2 || algo == 3) && !eb::phik_dmma_supported(p->nx, p->ny))
     return fail(EB_ERR_UNSUPPORTED, "the register-streamed DMMA phi_k kernel needs nx % 4 == 0 and nx >= 128");
   if (algo >= 4 && (!eb::phik_tma_supported(p->nx, p->ny) || !eb::phik_tma_encoder()))
@@ -355,6 +363,17 @@ static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* ph
   EB_TRACE("eb_phik_execute");
   EB_CUDA(cudaSetDevice(p->device));
   int algo = p->algo;
+  if (p->nb > 32)
+  {
+    // wide route: the simple pair over blocks of 32 orders, then the normalisation
+    const int ld = p->ld;
+    eb::phik_stage1_simple<<<dim3(p->ny, ld / 32), 256, 0, p->stream>>>(phi_dev, p->nx, p->d_cx, ld, p->d_T);
+    eb::phik_stage2_simple<<<dim3(p->nb, ld / 32), 256, 0, p->stream>>>(p->d_T, p->ny, p->d_cy, ld, p->d_parts);
+    eb::phik_finalize_wide<<<(ld * ld + 255) / 256, 256, 0, p->stream>>>(p->d_parts, p->nb, ld, phik_dev, phi_sum_dev, raw_dev);
+    p->launches += 3;
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+  }
   const bool big = (long long)p->nx * p->ny >= (1 << 18);
   if (algo == 0)
     algo = (big && eb::phik_tma_supported(p->nx, p->ny) && eb::phik_tma_encoder() && (reinterpret_cast<uintptr_t>(phi_dev) & 15) == 0) ? 4 :
@@ -381,8 +400,8 @@ static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* ph
   }
   else
   {
-    eb::phik_stage1_simple<<<p->ny, 256, 0, p->stream>>>(phi_dev, p->nx, p->d_cx, p->d_T);
-    eb::phik_stage2_simple<<<32, 256, 0, p->stream>>>(p->d_T, p->ny, p->d_cy, p->d_parts);
+    eb::phik_stage1_simple<<<p->ny, 256, 0, p->stream>>>(phi_dev, p->nx, p->d_cx, eb::kPhikLd, p->d_T);
+    eb::phik_stage2_simple<<<32, 256, 0, p->stream>>>(p->d_T, p->ny, p->d_cy, eb::kPhikLd, p->d_parts);
     p->launches += 2;
   }
   eb::phik_finalize<<<1, 1024, 0, p->stream>>>(p->d_parts, nparts, p->nb, fold ? 1 : 0, phik_dev, phi_sum_dev, raw_dev);
@@ -453,6 +472,8 @@ struct eb_controller
   double *d_phik = nullptr, *d_lamk = nullptr;
   double *d_u0 = nullptr, *d_metric = nullptr, *d_ck = nullptr, *d_x = nullptr;
   double* d_xt = nullptr;                  // [B][N][3] staging of eb_opt_traj_host (allocated on first use, kept)
+  double* d_big_scratch = nullptr;         // num_basis > 32: [big_rows][K], one row per resident CTA of solve_kernel_big
+  int big_rows = 0;
   int *d_mem_idx_in = nullptr, *d_mem_idx_out = nullptr;
   int *h_fault = nullptr, *d_fault = nullptr;  // pinned + mapped: the kernels set it, the host reads it after a sync
   int last_idx_count = 0;
@@ -603,10 +624,47 @@ struct SolveLaunch
   }
 };
 
+// num_basis > 32: a CTA per instance (solve_kernel_big.cuh), persistent over the batch; one scratch row per CTA
+template <int MODEL>
+cudaError_t launch_solve_big(const eb::SolveParams& p, cudaStream_t s)
+{
+  const size_t bytes = eb::solve_big_smem_bytes(p.nb, p.N);
+  static size_t configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes > configured[dev & 63])
+  {
+    cudaError_t e = cudaFuncSetAttribute(eb::solve_kernel_big<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    configured[dev & 63] = bytes;
+  }
+  if (!p.big_scratch || p.big_rows < 1) return cudaErrorInvalidValue;
+  const int grid = std::min(p.B, p.big_rows);
+  eb::solve_kernel_big<MODEL><<<grid, eb::kBigThreads, bytes, s>>>(p, p.big_scratch);
+  return cudaGetLastError();
+}
+
+// resident CTAs of solve_kernel_big on the current device (= scratch rows worth allocating)
+int solve_big_resident(int nb, int N)
+{
+  const size_t bytes = eb::solve_big_smem_bytes(nb, N);
+  int dev = 0, sms = 148, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaFuncSetAttribute(eb::solve_kernel_big<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eb::solve_kernel_big<0>, eb::kBigThreads, bytes) != cudaSuccess)
+  {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  return sms * std::max(1, per_sm);
+}
+
 template <int MODEL>
 cudaError_t launch_solve_m(const eb::SolveParams& p, int rounds, cudaStream_t s)
 {
   const int nb = p.nb;
+  if (nb > 32) return launch_solve_big<MODEL>(p, s);
   if (nb <= 8) return SolveLaunch<MODEL, 8, false>::launch(p, rounds, s);
   if (nb <= 12 && use_v2(nb))
     return nb <= 10 ? SolveLaunch<MODEL, 10, true>::launch(p, rounds, s) : SolveLaunch<MODEL, 12, true>::launch(p, rounds, s);
@@ -627,6 +685,7 @@ cudaError_t launch_solve_m(const eb::SolveParams& p, int rounds, cudaStream_t s)
 // dynamic shared memory of the solve kernel instantiation that serves `nb` (same dispatch as launch_solve_m)
 size_t solve_smem_for(int nb, int N)
 {
+  if (nb > 32) return eb::solve_big_smem_bytes(nb, N);
   if (nb <= 8) return SolveLaunch<0, 8, false>::smem(N);
   if (nb <= 12 && use_v2(nb)) return nb <= 10 ? SolveLaunch<0, 10, true>::smem(N) : SolveLaunch<0, 12, true>::smem(N);
   if (nb <= 10) return SolveLaunch<0, 10, false>::smem(N);
@@ -701,8 +760,8 @@ eb_status eb_create(const eb_config* cfg, eb_controller** out)
     return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: unknown model (only the 3-twist models SimpleCart and Omni "
                                          "can be driven by ErgodicControl)");
   if (cfg->batch < 1) return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: batch must be >= 1");
-  if (cfg->num_basis < 1 || cfg->num_basis > 32)
-    return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: num_basis must be in 1..32");
+  if (cfg->num_basis < 1 || cfg->num_basis > EB_MAX_NUM_BASIS)
+    return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: num_basis must be in 1.." + std::to_string(EB_MAX_NUM_BASIS));
   if (!(cfg->dt != 0.0) || !std::isfinite(cfg->horizon / cfg->dt))
     return fail(EB_ERR_INVALID_ARGUMENT, "eb_create: dt must be non-zero and finite");
   const unsigned steps = static_cast<unsigned>(std::abs(cfg->horizon / cfg->dt));  // :199
@@ -768,6 +827,13 @@ eb_status eb_create(const eb_config* cfg, eb_controller** out)
     for (int kx = 0; kx < c->nb; kx++)
       lam[ky * c->nb + kx] = 1.0 / std::pow(1.0 + std::sqrt((double)((long long)kx * kx + (long long)ky * ky)), 1.5);
   EB_CUDA_C(cudaMemcpy(c->d_lamk, lam.data(), sizeof(double) * c->K, cudaMemcpyHostToDevice));
+  if (c->nb > 32)
+  {  // solve_kernel_big: S = lamda .* (c_k - phi_k) of every resident CTA
+    c->big_rows = std::min(c->B, solve_big_resident(c->nb, c->N));
+    if (const char* e = std::getenv("EB_BIG_ROWS"))  // tests: fewer CTAs than instances on a small batch
+      c->big_rows = std::max(1, std::min(c->big_rows, std::atoi(e)));
+    EB_CUDA_C(cudaMalloc(&c->d_big_scratch, sizeof(double) * (size_t)c->K * (size_t)c->big_rows));
+  }
 #undef EB_CUDA_C
   *out = c;
   return EB_OK;
@@ -793,6 +859,7 @@ void eb_destroy(eb_controller* c)
   cudaFreeHost(c->h_fault);
   cudaFree(c->d_phi_grid);
   cudaFree(c->d_gauss);
+  cudaFree(c->d_big_scratch);
   eb_phik_plan_destroy(c->plan);
   delete c;
 }
@@ -1065,6 +1132,8 @@ eb_status eb_control_dev(eb_controller* c, double xmin, double xmax, double ymin
   p.metric = metric_dev;
   p.ck = c->keep_ck ? c->d_ck : nullptr;
   p.fault = c->d_fault;
+  p.big_scratch = c->d_big_scratch;
+  p.big_rows = c->big_rows;
   if (c->peer)
   {
     p.n_peer = c->peer->n_peer;
@@ -1252,8 +1321,8 @@ std::vector<double> pack_gaussians(int ng, const double* mu, const double* sigma
 static eb_status basis_sum(int device, double lx, double ly, int nb, const double* pts, int ld, long long n,
                            const double* w, double scale, double* out)
 {
-  if (nb < 1 || nb > 32 || n < 1 || !pts || !out || ld < 2)
-    return fail(EB_ERR_INVALID_ARGUMENT, "Basis: need 1 <= num_basis <= 32, at least one point, ld >= 2");
+  if (nb < 1 || nb > EB_MAX_NUM_BASIS || n < 1 || !pts || !out || ld < 2)
+    return fail(EB_ERR_INVALID_ARGUMENT, "Basis: need 1 <= num_basis <= " + std::to_string(EB_MAX_NUM_BASIS) + ", at least one point, ld >= 2");
   EB_CUDA(cudaSetDevice(device));
   DevBuf dp, dw, dout;
   EB_CUDA(dp.alloc((size_t)ld * n));
@@ -1285,7 +1354,7 @@ eb_status eb_basis_spatial_coeff_host(int device, double lx, double ly, int nb, 
 
 eb_status eb_basis_grad_host(int device, double lx, double ly, int nb, const double* x, double* dfk)
 {
-  if (nb < 1 || nb > 32 || !x || !dfk) return fail(EB_ERR_INVALID_ARGUMENT, "Basis::gradFourierBasis: bad argument");
+  if (nb < 1 || nb > EB_MAX_NUM_BASIS || !x || !dfk) return fail(EB_ERR_INVALID_ARGUMENT, "Basis::gradFourierBasis: bad argument");
   EB_CUDA(cudaSetDevice(device));
   DevBuf d;
   EB_CUDA(d.alloc(2 * (size_t)nb * nb));
@@ -2297,6 +2366,9 @@ eb_status eb_phik_execute_allreduce_dev(eb_phik_plan* p, eb_phik_peer* g, const 
   EB_TRACE("eb_phik_execute_allreduce_dev");
   if (!p || !g || !phi_dev || !phik_dev) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_execute_allreduce_dev: NULL argument");
   if (!g->connected) return fail(EB_ERR_INVALID_ARGUMENT, "eb_phik_execute_allreduce_dev: peer group is not connected");
+  if (p->nb > 32)
+    return fail(EB_ERR_UNSUPPORTED, "eb_phik_execute_allreduce_dev: the fused all-reduce exchanges 32 x 32 blocks (num_basis <= 32); "
+                                    "combine wider shards with eb_phik_execute_raw_dev + an all-reduce of the ld x ld block");
   if (!eb::phik_tma_supported(p->nx, p->ny) || !eb::phik_tma_encoder() || (reinterpret_cast<uintptr_t>(phi_dev) & 15) != 0)
     return fail(EB_ERR_UNSUPPORTED, "eb_phik_execute_allreduce_dev: needs the TMA tile kernel (even nx >= 64, aligned density)");
   const int par = (int)(g->step & 1);
@@ -2351,8 +2423,9 @@ eb_status eb_map_target_create(int device, unsigned int xsize, unsigned int ysiz
 {
   if (!out) return fail(EB_ERR_INVALID_ARGUMENT, "eb_map_target_create: out is NULL");
   *out = nullptr;
-  if (xsize < 1 || ysize < 1 || !(resolution > 0.0) || nb < 1 || nb > 32)
-    return fail(EB_ERR_INVALID_ARGUMENT, "eb_map_target_create: need xsize, ysize >= 1, resolution > 0, 1 <= nb <= 32");
+  if (xsize < 1 || ysize < 1 || !(resolution > 0.0) || nb < 1 || nb > EB_MAX_NUM_BASIS)
+    return fail(EB_ERR_INVALID_ARGUMENT,
+                "eb_map_target_create: need xsize, ysize >= 1, resolution > 0, 1 <= nb <= " + std::to_string(EB_MAX_NUM_BASIS));
   if ((unsigned long long)xsize * ysize > 0x7fffffffull)
     return fail(EB_ERR_UNSUPPORTED, "eb_map_target_create: more than 2^31 - 1 cells");
   EB_CUDA(cudaSetDevice(device));
@@ -2372,7 +2445,7 @@ eb_status eb_map_target_create(int device, unsigned int xsize, unsigned int ysiz
     return st;
   }
   cudaError_t e = cudaMalloc(&m->d_lut, sizeof(double) * 256);
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_phik, sizeof(double) * 1024);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_phik, sizeof(double) * (size_t)std::max(1024, nb * nb));
   if (e == cudaSuccess) e = cudaMalloc(&m->d_sum, sizeof(double));
   if (e == cudaSuccess)
   {

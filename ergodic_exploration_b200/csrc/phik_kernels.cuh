@@ -8,23 +8,26 @@
 // and since F_0 == 1, sum(Phi) = phi_raw[0]: normalising the density
 // (target.cpp:87) is one division after the contraction.
 //
-// This file holds the shape-agnostic kernels (any nx, ny, nb <= 32); the
-// DMMA/TMA tile kernel for large grids is in phik_dmma.cuh.
+// This file holds the shape-agnostic kernels (any nx, ny, nb); the DMMA/TMA
+// tile kernels for large grids (nb <= 32) are in phik_dmma.cuh / phik_tma.cuh.
+// Tables and T have a leading dimension ld: 32 for nb <= 32 (what the tile
+// kernels expect), nb rounded up to a multiple of 32 beyond that.
 #pragma once
 
 #include "common.cuh"
 
 namespace eb
 {
-constexpr int kPhikLd = 32;  // leading dimension of the cosine tables / T (bases padded to 32)
+constexpr int kPhikLd = 32;  // leading dimension of the cosine tables / T for nb <= 32 (bases padded to 32)
+__host__ __device__ inline int phik_ld(int nb) { return nb <= 32 ? kPhikLd : ((nb + 31) & ~31); }
 
 // tab[j][k] = cos(k * (PI / l) * coord[j]) for k < nb, else 0 (basis.cpp:85)
-__global__ void cos_table_kernel(const double* __restrict__ coord, int n, double freq, int nb,
+__global__ void cos_table_kernel(const double* __restrict__ coord, int n, double freq, int nb, int ld,
                                  double* __restrict__ tab)
 {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * kPhikLd) return;
-  const int j = idx / kPhikLd, k = idx % kPhikLd;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * ld) return;
+  const int j = (int)(idx / ld), k = (int)(idx % ld);
   tab[idx] = k < nb ? cos((double)k * freq * coord[j]) : 0.0;
 }
 
@@ -49,43 +52,57 @@ __global__ void target_fill_kernel(int ng, const double* __restrict__ gauss, con
   phi[c] = val;
 }
 
-// stage 1: T[i][kx] = sum_j Phi[i][j] * Cx[j][kx]; one CTA (32 x 8 threads) per row
+// stage 1: T[i][kx] = sum_j Phi[i][j] * Cx[j][kx]; one CTA (32 x 8 threads) per (row, block of 32 orders)
 __global__ void __launch_bounds__(256) phik_stage1_simple(const double* __restrict__ phi, int nx,
-                                                          const double* __restrict__ cx, double* __restrict__ T)
+                                                          const double* __restrict__ cx, int ld, double* __restrict__ T)
 {
-  __shared__ double red[8][kPhikLd];
-  const int kx = threadIdx.x & 31, part = threadIdx.x >> 5;
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5, kx = blockIdx.y * 32 + lane;
   const double* row = phi + (size_t)blockIdx.x * nx;
   double acc = 0.0;
-  for (int j = part; j < nx; j += 8) acc = fma(row[j], cx[(size_t)j * kPhikLd + kx], acc);
-  red[part][kx] = acc;
+  for (int j = part; j < nx; j += 8) acc = fma(row[j], cx[(size_t)j * ld + kx], acc);
+  red[part][lane] = acc;
   __syncthreads();
   if (part == 0)
   {
-    double s = red[0][kx];
+    double s = red[0][lane];
 #pragma unroll
-    for (int pth = 1; pth < 8; pth++) s += red[pth][kx];
-    T[(size_t)blockIdx.x * kPhikLd + kx] = s;
+    for (int pth = 1; pth < 8; pth++) s += red[pth][lane];
+    T[(size_t)blockIdx.x * ld + kx] = s;
   }
 }
 
-// stage 2: raw[ky][kx] = sum_i Cy[i][ky] * T[i][kx]; one CTA per ky
+// stage 2: raw[ky][kx] = sum_i Cy[i][ky] * T[i][kx]; one CTA per (ky, block of 32 orders kx)
 __global__ void __launch_bounds__(256) phik_stage2_simple(const double* __restrict__ T, int ny,
-                                                          const double* __restrict__ cyt, double* __restrict__ raw)
+                                                          const double* __restrict__ cyt, int ld, double* __restrict__ raw)
 {
-  __shared__ double red[8][kPhikLd];
-  const int kx = threadIdx.x & 31, part = threadIdx.x >> 5, ky = blockIdx.x;
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5, ky = blockIdx.x, kx = blockIdx.y * 32 + lane;
   double acc = 0.0;
-  for (int i = part; i < ny; i += 8) acc = fma(cyt[(size_t)i * kPhikLd + ky], T[(size_t)i * kPhikLd + kx], acc);
-  red[part][kx] = acc;
+  for (int i = part; i < ny; i += 8) acc = fma(cyt[(size_t)i * ld + ky], T[(size_t)i * ld + kx], acc);
+  red[part][lane] = acc;
   __syncthreads();
   if (part == 0)
   {
-    double s = red[0][kx];
+    double s = red[0][lane];
 #pragma unroll
-    for (int pth = 1; pth < 8; pth++) s += red[pth][kx];
-    raw[ky * kPhikLd + kx] = s;
+    for (int pth = 1; pth < 8; pth++) s += red[pth][lane];
+    raw[(size_t)ky * ld + kx] = s;
   }
+}
+
+// nb > 32: normalisation of the ld x ld raw block of the simple pair; phik[ky*nb + kx] = raw[ky][kx] / raw[0][0]
+__global__ void phik_finalize_wide(const double* __restrict__ parts, int nb, int ld, double* __restrict__ phik,
+                                   double* __restrict__ phi_sum, double* __restrict__ raw)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ld * ld) return;
+  const double total = parts[0];
+  const int ky = t / ld, kx = t % ld;
+  const bool in = ky < nb && kx < nb;
+  if (raw) raw[t] = in ? parts[t] : 0.0;
+  if (phik && in) phik[ky * nb + kx] = parts[t] / total;
+  if (t == 0 && phi_sum) *phi_sum = total;
 }
 
 // sums `nparts` partial 32x32 blocks in a fixed order (deterministic) and

@@ -133,6 +133,9 @@ struct SolveParams
   unsigned int* done_counter;                // warps of this launch that have published their row
   const unsigned long long* my_flags;        // this rank's own arrival flags [n_peer] ...
   unsigned long long need;                   // ... must all have reached this before the buffer is reused
+  // num_basis > 32 (solve_kernel_big.cuh): one row of nb * nb doubles per resident CTA, and how many rows there are
+  double* big_scratch;
+  int big_rows;
 };
 
 // The first twist of one instance: lanes 0..2 store one contiguous 24-byte segment (u0 may live in mapped host

@@ -58,8 +58,11 @@ typedef enum eb_model {
 
 /* Constructor arguments of ErgodicControl (ergodic_control.hpp:90-94) plus
  * the two constants the reference hard-codes in gradBarrier (:457-458). */
-/* DEVIATION: num_basis is limited to 1..32 (the reference accepts any count, basis.cpp:48-77): the coefficient block
- * of one instance lives in the registers of one warp.  eb_create returns EB_ERR_INVALID_ARGUMENT beyond that. */
+/* num_basis: 1..EB_MAX_NUM_BASIS (the reference accepts any count, basis.cpp:48-77).  Up to 32 the coefficient block of
+ * an instance lives in the registers of one warp (the tuned kernels); 33..128 run a CTA per instance with the block
+ * spread over its threads (csrc/solve_kernel_big.cuh) and the phi_k contraction over blocks of 32 orders.  Beyond 128
+ * the cosine tables of 32 states no longer fit shared memory: eb_create returns EB_ERR_INVALID_ARGUMENT. */
+#define EB_MAX_NUM_BASIS 128
 typedef struct eb_config {
   int model;            /* eb_model */
   int batch;            /* B >= 1 independent instances */
@@ -68,7 +71,7 @@ typedef struct eb_config {
   double horizon;       /* control horizon; steps = (unsigned)|horizon/dt| (:199) */
   double resolution;    /* target grid resolution (m) */
   double expl_weight;   /* exploration_weight */
-  unsigned num_basis;   /* cosine bases per dimension, 1..32 */
+  unsigned num_basis;   /* cosine bases per dimension, 1..EB_MAX_NUM_BASIS */
   unsigned buffer_size; /* max past states kept per instance (ReplayBuffer) */
   unsigned batch_size;  /* past states sampled per control() */
   double Rinv[9];       /* 3x3 column-major */
@@ -198,8 +201,8 @@ eb_status eb_phik_plan_fold(const eb_phik_plan *p, int *fold, double *deviation)
 eb_status eb_phik_execute_dev(eb_phik_plan *p, const double *phi_dev, double *phik_dev,
                               double *phi_sum_dev);
 eb_status eb_phik_execute_host(eb_phik_plan *p, const double *phi, double *phik, double *phi_sum);
-/* un-normalised contraction: raw[ky*32 + kx] = (C_y^T phi C_x)[ky][kx], 1024
- * doubles (entries with ky or kx >= nb are 0); raw[0] = sum(phi) */
+/* un-normalised contraction: raw[ky*ld + kx] = (C_y^T phi C_x)[ky][kx], ld * ld doubles with ld = 32 for nb <= 32
+ * (1024 doubles) and nb rounded up to a multiple of 32 beyond (entries with ky or kx >= nb are 0); raw[0] = sum(phi) */
 eb_status eb_phik_execute_raw_dev(eb_phik_plan *p, const double *phi_dev, double *raw_dev);
 /* one-shot convenience (host buffers): plan + execute + destroy */
 eb_status eb_phik_from_grid_host(int device, const double *phi, int nx, int ny, double resolution,

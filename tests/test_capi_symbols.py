@@ -61,7 +61,7 @@ def test_argument_validation_needs_no_gpu(lib):
     cfg.horizon = 0.1  # one step: the reference throws std::invalid_argument (ergodic_control.hpp:212-216)
     assert lib.eb_create(C.byref(cfg), C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
     assert b"two steps" in lib.eb_last_error()
-    cfg.horizon, cfg.num_basis = 5.0, 33
+    cfg.horizon, cfg.num_basis = 5.0, 129  # EB_MAX_NUM_BASIS = 128
     assert lib.eb_create(C.byref(cfg), C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
     cfg.num_basis, cfg.model = 10, 7
     assert lib.eb_create(C.byref(cfg), C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
@@ -69,7 +69,7 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.eb_control_host(None, 0, 1, 0, 1, None, None, None, None) == capi.EB_ERR_INVALID_ARGUMENT
     # round-2 entry points
     assert lib.eb_map_target_create(0, 0, 10, 0.05, 8, C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
-    assert lib.eb_map_target_create(0, 10, 10, 0.05, 33, C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
+    assert lib.eb_map_target_create(0, 10, 10, 0.05, 129, C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
     assert lib.eb_rk4_solve_host(0, 7, None, 0.1, 1.0, None, None, 0, 1, None) == capi.EB_ERR_INVALID_ARGUMENT
     assert lib.eb_model_eval_host(0, 2, None, None, None, 1, None, None, None, None) == capi.EB_ERR_INVALID_ARGUMENT  # Cart needs params
     assert [lib.eb_model_controls(m) for m in range(5)] == [3, 3, 2, 4, 0]

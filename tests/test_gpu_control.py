@@ -278,6 +278,57 @@ def test_every_basis_count_path(nb):
     _compare_step(gpu, orcs, BOUNDS_10, x, tag=f"nb={nb}")
 
 
+@pytest.mark.parametrize("nb", [33, 40, 64, 100])
+def test_wide_basis_counts(nb):
+    """num_basis > 32 (the reference accepts any count, basis.cpp:48-77): the CTA-per-instance kernel
+    (csrc/solve_kernel_big.cuh) and the phi_k contraction over blocks of 32 orders"""
+    rng = np.random.default_rng(300 + nb)
+    B, model = 3, MODEL_OMNI if nb % 2 else MODEL_SIMPLE_CART
+    gpu = make_gpu(model, B, nb=nb, horizon=3.5)
+    orcs = [make_oracle(model, nb=nb, horizon=3.5) for _ in range(B)]
+    x = random_states(rng, B)
+    ut = warm_ut(rng, B, gpu.steps, model)
+    gpu.set_ut(ut)
+    for i, o in enumerate(orcs):
+        o.set_ut(ut[i])
+    for past in (random_states(rng, B) for _ in range(37)):
+        gpu.addStateMemory(past)
+        for i, o in enumerate(orcs):
+            o.add_state_memory(past[i])
+    u0 = _compare_step(gpu, orcs, BOUNDS_10, x, tag=f"nb={nb}")
+    assert_coeff_close(gpu.get_phik()[0], orcs[0].get_phik(), f"nb={nb} phi_k")
+    _compare_step(gpu, orcs, BOUNDS_10, plant(x, u0), tag=f"nb={nb} step 2")
+
+
+def test_wide_basis_persistent_ctas_and_sampled_memory(monkeypatch):
+    """fewer resident CTAs than instances (every CTA walks several instances) with more stored states than
+    batch_size (explicit sample indices), two 32-step rounds"""
+    monkeypatch.setenv("EB_BIG_ROWS", "2")
+    rng = np.random.default_rng(36)
+    B, nb, model = 7, 36, MODEL_OMNI
+    gpu = make_gpu(model, B, nb=nb, horizon=4.0, batch_size=20)
+    orcs = [make_oracle(model, nb=nb, horizon=4.0, batch_size=20) for _ in range(B)]
+    x = random_states(rng, B)
+    ut = warm_ut(rng, B, gpu.steps, model)
+    gpu.set_ut(ut)
+    for i, o in enumerate(orcs):
+        o.set_ut(ut[i])
+    for past in (random_states(rng, B) for _ in range(45)):
+        gpu.addStateMemory(past)
+        for i, o in enumerate(orcs):
+            o.add_state_memory(past[i])
+    idx = rng.integers(0, 45, size=(B, 20)).astype(np.int32)
+    _compare_step(gpu, orcs, BOUNDS_10, x, mem_idx=idx, tag="nb=36 sampled")
+    # the on-device sampler: replay its indices through the oracle
+    metric = np.empty(B)
+    x2 = random_states(rng, B)
+    u0 = gpu.control(BOUNDS_10, x2, metric=metric)
+    used = gpu.last_mem_idx()
+    ou0, _, ometric, _ = _oracle_step(orcs, BOUNDS_10, x2, used)
+    assert_abs_rel_close(u0, ou0, "nb=36 device sampler u0")
+    assert_abs_rel_close(metric, ometric, "nb=36 device sampler metric")
+
+
 def test_long_horizon_many_rounds():
     """200 horizon steps = 7 rounds of 32 time-step lanes"""
     rng = np.random.default_rng(77)

@@ -38,6 +38,10 @@ def gaussian_mixture(rng, nx, ny, res, ng=8):
     (136, 70, 32, 2),     # fold, nx / 2 = 68: ragged folded chunk
     (136, 70, 32, 3),
     (2056, 130, 31, 2),   # fold, several units per row block, odd basis count
+    (101, 101, 33, 0),    # num_basis > 32: the simple pair over blocks of 32 orders
+    (160, 90, 64, 1),
+    (77, 130, 100, 0),
+    (640, 512, 48, 0),    # a grid the tile kernels would take at nb <= 32
 ])
 def test_phik_matches_oracle(nx, ny, nb, algo):
     from ergodic_exploration_b200 import PhikPlan
@@ -113,10 +117,33 @@ def test_phik_linearity_large():
     assert_coeff_close(pab * sab, pa * sa + pb * sb, "linearity")
 
 
+def test_phik_wide_raw_block_and_tile_algos_refused():
+    """num_basis > 32: the raw block has leading dimension nb rounded up to 32; the 32-order tile kernels say no"""
+    import torch
+
+    from ergodic_exploration_b200 import ErgodicB200Error, PhikPlan, capi
+
+    rng = np.random.default_rng(5)
+    nx, ny, nb, res = 128, 64, 40, 0.1
+    phi = rng.random((ny, nx))
+    lx, ly = (nx - 1) * res, (ny - 1) * res
+    plan = PhikPlan(nx, ny, res, lx, ly, nb)
+    raw = torch.full((64, 64), np.nan, dtype=torch.float64, device="cuda")
+    plan.execute_raw(torch.from_numpy(phi).cuda(), raw=raw)
+    raw = raw.cpu().numpy()
+    want, total = Oracle.phik_from_grid(phi, res, lx, ly, nb)
+    assert_coeff_close(raw[:nb, :nb].ravel() / raw[0, 0], want, "raw block nb=40")
+    assert abs(raw[0, 0] - total) <= 1e-9 * total
+    assert np.all(raw[nb:, :] == 0.0) and np.all(raw[:, nb:] == 0.0)
+    with pytest.raises(ErgodicB200Error) as e:
+        PhikPlan(nx, ny, res, lx, ly, nb, algo=4)
+    assert e.value.status == capi.EB_ERR_UNSUPPORTED
+
+
 def test_plan_rejects_bad_arguments():
     from ergodic_exploration_b200 import PhikPlan
 
     with pytest.raises(ValueError):
-        PhikPlan(16, 16, 0.1, 1.5, 1.5, 33)
+        PhikPlan(16, 16, 0.1, 1.5, 1.5, 129)  # EB_MAX_NUM_BASIS = 128
     with pytest.raises(ValueError):
         PhikPlan(0, 16, 0.1, 1.5, 1.5, 4)
