@@ -262,8 +262,13 @@ def run_reference(args, rank, world):
         "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "instances_per_step": sample,
-                   "note": "reference CPU path (single-threaded per instance), all host cores"},
+        # the GPU arm's workload keys, same names and values (bench_solve); the CPU arm's own facts go under other keys
+        "config": {"workload": wl["desc"], "instances_per_gpu": wl["batch"] if wl["scaling"] == "weak" else -(-wl["batch"] // world),
+                   "instances_total": wl["batch"] * world if wl["scaling"] == "weak" else wl["batch"],
+                   "num_basis": wl["nb"], "horizon_steps": int(abs(wl["horizon"] / DT)), "replay_states": wl["mem"],
+                   "instances_per_step": sample,
+                   "note": "reference CPU path (single-threaded per instance), all host cores; each step is a bounded "
+                           "sample of the workload's instances"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -3,12 +3,12 @@
 // The reference accepts any basis count (basis.cpp:48-77).  The warp-per-instance kernels (solve_kernel.cuh,
 // solve_kernel_v2.cuh) keep an instance's nb x nb coefficient block in ONE warp's registers, which stops at
 // nb = 32; this kernel gives an instance a whole CTA instead: the coefficient block is spread over the CTA's
-// threads as 4 x 4 register tiles, S = lamda .* (c_k - phi_k) goes through an L2-resident scratch row per
-// resident CTA, and the metric gradient is evaluated from order-major cos / sin tables of 32 steps at a time with
-// the ky range split over the CTA's warps.  Same arithmetic contract, parameter block, error bits and outputs as
-// solve_kernel (read its header first); the rollout and the co-state pass are the same three warp scans, run by
-// warp 0.  Plain DFMA: at these sizes the work per instance (~ 6 nb^2 (N + M) flops) is large enough that the
-// kernel is FP64-pipe-bound without tensor-core tiles.
+// warps as DMMA accumulator strips, S = lamda .* (c_k - phi_k) goes through an L2-resident scratch row per
+// resident CTA, and both contractions run on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA.8x8x4) from order-major
+// cos / sin tables of 32 states at a time: c_k as rank-32 updates of 8 x 64 coefficient strips (one strip per warp
+// and pass), the metric gradient as the products of a warp's 8 coefficient rows with the x tables of 32 steps.
+// Same arithmetic contract, parameter block, error bits and outputs as solve_kernel (read its header first); the
+// rollout and the co-state pass are the same three warp scans, run by warp 0.
 //
 // Replaces, per instance: ErgodicControl::control() (ergodic_control.hpp:225-311) with Basis::trajCoeff
 // (basis.cpp:109-120), gradErgodicMetric (:419-436), gradBarrier (:454-474), the backward RK4 (integrator.hpp:154-194,
@@ -23,17 +23,13 @@ constexpr int kBigThreads = 256;
 constexpr int kBigWarps = kBigThreads / 32;
 constexpr int kBigMaxBasis = 128;  // EB_MAX_NUM_BASIS (ergodic_b200.h): tables of 32 states fit shared memory
 
-// c_k tables, state-major: row = one state's cos(k . ) for k < nb, padded with zeros to a multiple of 4 (+2: rows
-// stay 16-byte aligned and consecutive rows start 4 banks apart)
-__host__ __device__ inline int big_pitch(int nb) { return ((nb + 3) & ~3) + 2; }
-// shared memory (doubles): per-step records [4][npad], e_x | e_y [2][npad], the table region (four order-major
-// gradient tables [nb][32]; the two c_k tables and the tile reduction buffer alias it), the per-warp partial
-// gradient sums [8][32][2] and the metric partials
-__host__ __device__ inline int big_tab_doubles(int nb)
-{
-  const int grad = 4 * nb * 32, ck = 2 * 32 * big_pitch(nb), red = 16 * 128;
-  return grad > ck ? (grad > red ? grad : red) : (ck > red ? ck : red);
-}
+// order-major tables: row = one order's cos / sin over the 32 states of a chunk; pitch 36 = 32 + 4 -> the DMMA
+// fragment loads (8 rows x 4 states, or 4 rows x 8 states) touch every bank pair exactly twice: 2 wavefronts, the minimum
+constexpr int kBigPitch = 36;
+__host__ __device__ inline int big_tab_rows(int nb) { return (nb + 7) & ~7; }  // orders padded to whole 8-row tiles (zeros)
+// shared memory (doubles): per-step records [4][npad], e_x | e_y [2][npad], the table region (four gradient tables
+// [rows][36]; the two c_k tables alias the first two), the per-warp partial gradient sums [8][32][2], the metric partials
+__host__ __device__ inline int big_tab_doubles(int nb) { return 4 * big_tab_rows(nb) * kBigPitch; }
 inline size_t solve_big_smem_bytes(int nb, int N)
 {
   const int npad = ((N + 31) / 32) * 32;
@@ -74,18 +70,17 @@ __global__ void __launch_bounds__(kBigThreads) solve_kernel_big(const SolveParam
   const int rounds = (p.N + 31) >> 5;
   const int npad = rounds * 32;
   const int nb = p.nb, K = nb * nb;
-  const int pitch = big_pitch(nb);
   double* const rec = smem;                 // [4][npad]: heading cos, sin; Fourier-frame x, y
   double* const exy = rec + 4 * npad;       // [2][npad]: e_x, e_y of every step
   double* const tab = exy + 2 * npad;       // table region
   double* const part = tab + big_tab_doubles(nb);  // [8 warps][32 steps][2]
   double* const mred = part + 2 * 32 * kBigWarps;  // [8] metric partials
   double* const S = scratch + (size_t)blockIdx.x * K;
-  const int ntx = (nb + 3) >> 2, ntiles = ntx * ntx;
-  // fewer tiles than threads: the spare threads take every G-th state of a chunk (summed in a fixed order below)
-  const int G = ntiles >= kBigThreads ? 1 : min(kBigThreads / ntiles, 4);
+  const int tabrows = big_tab_rows(nb), Tt = tabrows >> 3;  // 8 x 8 coefficient tiles per axis
+  const int ntb = (Tt + 7) >> 3;                             // strips of up to 8 tiles per tile row
+  const int nunits = Tt * ntb, npass = (nunits + kBigWarps - 1) / kBigWarps;
   const int T = p.M + p.N;
-  const int kq = (nb + 3) >> 2;  // orders per table-builder segment
+  const int kq = tabrows >> 2;  // table rows per builder segment (4 segments)
 
   grid_dependency_wait();
   for (int inst = blockIdx.x; inst < p.B; inst += gridDim.x)
@@ -127,26 +122,29 @@ __global__ void __launch_bounds__(kBigThreads) solve_kernel_big(const SolveParam
     __syncthreads();
 
     // ---- c_k = (1/T) sum_t cos(ky b y_t) cos(kx a x_t) over the sampled past states and the horizon
-    //      (basis.cpp:109-120), S = lamda .* (c_k - phi_k) (:422), ergodic metric ------------------------------
+    //      (basis.cpp:109-120), S = lamda .* (c_k - phi_k) (:422), ergodic metric.  Order-major cosine tables of 32
+    //      states at a time; a warp owns the 8 x 64 coefficient strip (ti, 8 tj) of a pass and runs 8 DMMA k-steps
+    //      per chunk over it (fragments as in solve_kernel's coeff_chunk) -------------------------------------------
     double metric = 0.0;
-    for (int tile0 = 0; tile0 < ntiles; tile0 += kBigThreads)
+    const int g = lane >> 2, q = lane & 3;
+    double* const t_x = tab;                  // cos(kx a x_s)   [8 T][kBigPitch]
+    double* const t_y = tab + tabrows * kBigPitch;  // cos(ky b y_s)
+    for (int pass = 0; pass < npass; pass++)
     {
-      const int grp = G > 1 ? tid / ntiles : 0;
-      const int tile = G > 1 ? tid % ntiles : tile0 + tid;
-      const bool active = tile < ntiles && grp < G;
-      const int ty = active ? tile / ntx : 0, tx = active ? tile % ntx : 0;
-      double acc[4][4];
+      const int unit = pass * kBigWarps + warp;
+      const bool active = unit < nunits;
+      const int ti = active ? unit / ntb : 0, tj0 = active ? 8 * (unit % ntb) : 0;
+      const int ntj = active ? min(8, Tt - tj0) : 0;
+      double acc[8][2];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+      for (int j = 0; j < 8; j++) acc[j][0] = acc[j][1] = 0.0;
       for (int s0 = 0; s0 < T; s0 += 32)
       {
         __syncthreads();  // the previous chunk's tables have been read
         {
           // table builders: thread = (state, axis, quarter of the orders)
-          const int st = lane, axis = warp & 1, seg = warp >> 1;
-          const int s = s0 + st;
+          const int axis = warp & 1, seg = warp >> 1;
+          const int s = s0 + lane;
           const bool valid = s < T;
           double coord = 0.0;
           if (valid)
@@ -167,7 +165,7 @@ __global__ void __launch_bounds__(kBigThreads) solve_kernel_big(const SolveParam
                 atomicOr(p.fault, 2);
                 idx = 0;
               }
-              if (p.idx_mode != 0 && p.mem_idx_out && warp == 0 && tile0 == 0)
+              if (p.idx_mode != 0 && p.mem_idx_out && warp == 0 && pass == 0)
                 p.mem_idx_out[(size_t)inst * p.batch_size + s] = (int)idx;
               const double* h = p.hist + ((size_t)idx * p.B + inst) * 3;
               coord = h[axis] - (axis ? p.ymin : p.xmin);
@@ -176,68 +174,47 @@ __global__ void __launch_bounds__(kBigThreads) solve_kernel_big(const SolveParam
               coord = rec[(2 + axis) * npad + (s - p.M)];
           }
           const double u = coord * (axis ? p.inv_ly : p.inv_lx);
-          const int k0 = seg * kq, k1 = min(nb, k0 + kq);
-          double* const row = tab + (axis * 32 + st) * pitch;
+          const int k0 = seg * kq, k1 = min(tabrows, k0 + kq);
+          double* const col = (axis ? t_y : t_x) + lane;
           BigChain ch = big_chain_start(u, k0);
           for (int k = k0; k < k1; k++)
           {
-            row[k] = valid ? ch.ck : 0.0;  // states past the end contribute nothing
+            col[k * kBigPitch] = (valid && k < nb) ? ch.ck : 0.0;  // states past the end and padding orders: zero
             big_chain_step(ch);
           }
-          if (seg == 3)
-            for (int k = nb; k < pitch; k++) row[k] = 0.0;
         }
         __syncthreads();
         if (active)
         {
-          const double* const ry = tab + 32 * pitch + 4 * ty;
-          const double* const rx = tab + 4 * tx;
-          for (int st = grp; st < 32; st += G)
+          const int ksteps = (min(32, T - s0) + 3) >> 2;
+          const double* const fa = t_y + (8 * ti + g) * kBigPitch + q;
+          const double* const fb = t_x + (8 * tj0 + g) * kBigPitch + q;
+          for (int ks = 0; ks < ksteps; ks++)
           {
-            const double2 a01 = *reinterpret_cast<const double2*>(ry + st * pitch);
-            const double2 a23 = *reinterpret_cast<const double2*>(ry + st * pitch + 2);
-            const double2 b01 = *reinterpret_cast<const double2*>(rx + st * pitch);
-            const double2 b23 = *reinterpret_cast<const double2*>(rx + st * pitch + 2);
-            const double a[4] = { a01.x, a01.y, a23.x, a23.y }, b[4] = { b01.x, b01.y, b23.x, b23.y };
+            const double a = fa[4 * ks];
+            double b[8];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 8; j++) b[j] = j < ntj ? fb[j * 8 * kBigPitch + 4 * ks] : 0.0;
 #pragma unroll
-              for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            for (int j = 0; j < 8; j++)
+              if (j < ntj) dmma884(acc[j][0], acc[j][1], a, b[j]);
           }
         }
       }
-      if (G > 1)
-      {
-        // groups 1 .. G-1 hand their tiles to group 0, one group at a time (fixed order)
-        for (int g = 1; g < G; g++)
-        {
-          __syncthreads();
-          if (active && grp == g)
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-              for (int j = 0; j < 4; j++) tab[(i * 4 + j) * 128 + tile] = acc[i][j];
-          __syncthreads();
-          if (active && grp == 0)
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-              for (int j = 0; j < 4; j++) acc[i][j] += tab[(i * 4 + j) * 128 + tile];
-        }
-      }
-      if (active && grp == 0)
+      if (active)
       {
         const double inv_t = 1.0 / (double)T;  // basis.cpp:119
+        const int ky = 8 * ti + g;
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 8; j++)
 #pragma unroll
-          for (int j = 0; j < 4; j++)
+          for (int e = 0; e < 2; e++)
           {
-            const int ky = 4 * ty + i, kx = 4 * tx + j;
-            if (ky < nb && kx < nb)
+            const int kx = 8 * (tj0 + j) + 2 * q + e;
+            if (j < ntj && ky < nb && kx < nb)
             {
               const int k = ky * nb + kx;
-              const double c = __dmul_rn(inv_t, acc[i][j]);
+              const double c = __dmul_rn(inv_t, acc[j][e]);
               const double d = __dsub_rn(c, __ldg(p.phik + k));
               const double sv = __ldg(p.lamk + k) * d;
               metric += sv * d;
@@ -257,12 +234,15 @@ __global__ void __launch_bounds__(kBigThreads) solve_kernel_big(const SolveParam
       p.metric[inst] = m;
     }
 
-    // ---- gradient of the ergodic metric (:419-436), 32 steps at a time: e_x = sum_ky cos(ky b y) sum_kx S a_kx
-    //      sin(kx a x), e_y = sum_ky b_ky sin(ky b y) sum_kx S cos(kx a x); lanes = steps, warps = ky ranges -----
+    // ---- gradient of the ergodic metric (:419-436), 32 steps at a time: R1 = S (a_kx sin(kx a x_t)), R2 = S cos(kx a x_t)
+    //      as DMMA products of the warp's 8 coefficient rows with the order-major x tables (4 tiles of 8 steps), then
+    //      e_x = sum_ky cos(ky b y_t) R1[ky][t], e_y = sum_ky b_ky sin(ky b y_t) R2[ky][t]: fragment-wise product with
+    //      the y tables, a shuffle reduction over the 8 row lanes, and a sum over the warps in index order ------------
     double* const t_asx = tab;
-    double* const t_cx = tab + nb * 32;
-    double* const t_cy = tab + 2 * nb * 32;
-    double* const t_bsy = tab + 3 * nb * 32;
+    double* const t_cx = tab + tabrows * kBigPitch;
+    double* const t_cy = tab + 2 * tabrows * kBigPitch;
+    double* const t_bsy = tab + 3 * tabrows * kBigPitch;
+    const int gks = (nb + 3) >> 2;
     for (int r = 0; r < rounds; r++)
     {
       {
@@ -271,56 +251,89 @@ __global__ void __launch_bounds__(kBigThreads) solve_kernel_big(const SolveParam
         const double coord = rec[(2 + axis) * npad + i];
         const double u = coord * (axis ? p.inv_ly : p.inv_lx);
         const double f = axis ? p.by : p.ax;
-        const int k0 = seg * kq, k1 = min(nb, k0 + kq);
+        const int k0 = seg * kq, k1 = min(tabrows, k0 + kq);
         double* const tc = (axis ? t_cy : t_cx) + lane;
         double* const ts = (axis ? t_bsy : t_asx) + lane;
         BigChain ch = big_chain_start(u, k0);
         for (int k = k0; k < k1; k++)
         {
-          tc[k * 32] = ch.ck;
-          ts[k * 32] = ((double)k * f) * ch.sk;
+          tc[k * kBigPitch] = k < nb ? ch.ck : 0.0;
+          ts[k * kBigPitch] = k < nb ? ((double)k * f) * ch.sk : 0.0;
           big_chain_step(ch);
         }
       }
       __syncthreads();
       {
-        const int lo = (warp * nb) / kBigWarps, hi = ((warp + 1) * nb) / kBigWarps;
-        double ex = 0.0, ey = 0.0;
-        for (int ky = lo; ky < hi; ky += 4)
+        const int nnj = min(4, (min(32, p.N - r * 32) + 7) >> 3);  // 8-step tiles with at least one valid step
+        double v[4][2], w[4][2];  // e_x, e_y partial sums of steps 8 nj + 2 q + e over this lane's rows
+#pragma unroll
+        for (int nj = 0; nj < 4; nj++) v[nj][0] = v[nj][1] = w[nj][0] = w[nj][1] = 0.0;
+        for (int mi = warp; mi < Tt; mi += kBigWarps)
         {
-          const int nrow = min(4, hi - ky);
-          double rx[4] = { 0.0, 0.0, 0.0, 0.0 }, ry[4] = { 0.0, 0.0, 0.0, 0.0 };
-          const double* const s0 = S + (size_t)ky * nb;
-          for (int kx = 0; kx < nb; kx++)
+          const int ky = 8 * mi + g;
+          double R1[4][2], R2[4][2];
+#pragma unroll
+          for (int nj = 0; nj < 4; nj++) R1[nj][0] = R1[nj][1] = R2[nj][0] = R2[nj][1] = 0.0;
+          const double* const srow = S + (size_t)min(ky, nb - 1) * nb;
+          const bool row_ok = ky < nb;
+          double a = (row_ok && q < nb) ? srow[q] : 0.0;
+          for (int ks = 0; ks < gks; ks++)
           {
-            const double a = t_asx[kx * 32 + lane], c = t_cx[kx * 32 + lane];
+            const int kxn = 4 * (ks + 1) + q;
+            const double a_next = (row_ok && kxn < nb) ? srow[kxn] : 0.0;  // next k-step's fragment, ahead of the DMMAs
+            const double* const bs = t_asx + (4 * ks + q) * kBigPitch + g;
+            const double* const bc = t_cx + (4 * ks + q) * kBigPitch + g;
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-              if (q < nrow)
+            for (int nj = 0; nj < 4; nj++)
+              if (nj < nnj)
               {
-                const double sv = s0[q * nb + kx];  // warp-uniform address
-                rx[q] = fma(sv, a, rx[q]);
-                ry[q] = fma(sv, c, ry[q]);
+                dmma884(R1[nj][0], R1[nj][1], a, bs[8 * nj]);
+                dmma884(R2[nj][0], R2[nj][1], a, bc[8 * nj]);
               }
+            a = a_next;
           }
+          // lane (g, q) holds R[ky = 8 mi + g][steps 8 nj + 2 q, + 1]: weight with the y tables
+          const double* const yc = t_cy + ky * kBigPitch + 2 * q;
+          const double* const ys = t_bsy + ky * kBigPitch + 2 * q;
 #pragma unroll
-          for (int q = 0; q < 4; q++)
-            if (q < nrow)
+          for (int nj = 0; nj < 4; nj++)
+            if (nj < nnj)
             {
-              ex = fma(t_cy[(ky + q) * 32 + lane], rx[q], ex);
-              ey = fma(t_bsy[(ky + q) * 32 + lane], ry[q], ey);
+              const double2 c2 = *reinterpret_cast<const double2*>(yc + 8 * nj);
+              const double2 s2 = *reinterpret_cast<const double2*>(ys + 8 * nj);
+              v[nj][0] = fma(c2.x, R1[nj][0], v[nj][0]);
+              v[nj][1] = fma(c2.y, R1[nj][1], v[nj][1]);
+              w[nj][0] = fma(s2.x, R2[nj][0], w[nj][0]);
+              w[nj][1] = fma(s2.y, R2[nj][1], w[nj][1]);
             }
         }
-        part[(warp * 32 + lane) * 2 + 0] = ex;
-        part[(warp * 32 + lane) * 2 + 1] = ey;
+        // sum over the 8 row lanes (lane = 4 g + q): xor 4, 8, 16
+#pragma unroll
+        for (int nj = 0; nj < 4; nj++)
+#pragma unroll
+          for (int e = 0; e < 2; e++)
+          {
+            double sv = v[nj][e], sw = w[nj][e];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1)
+            {
+              sv += __shfl_xor_sync(kFull, sv, o);
+              sw += __shfl_xor_sync(kFull, sw, o);
+            }
+            if (g == 0)
+            {
+              part[(warp * 32 + 8 * nj + 2 * q + e) * 2 + 0] = sv;
+              part[(warp * 32 + 8 * nj + 2 * q + e) * 2 + 1] = sw;
+            }
+          }
       }
       __syncthreads();  // also: the tables may be rebuilt
       if (tid < 64)
       {
         const int st = tid & 31, which = tid >> 5;
-        double v = 0.0;
-        for (int w8 = 0; w8 < kBigWarps; w8++) v += part[(w8 * 32 + st) * 2 + which];
-        exy[which * npad + r * 32 + st] = -v * p.w;  // times expl_weight (:433)
+        double sum = 0.0;
+        for (int w8 = 0; w8 < kBigWarps; w8++) sum += part[(w8 * 32 + st) * 2 + which];
+        exy[which * npad + r * 32 + st] = -sum * p.w;  // times expl_weight (:433)
       }
     }
     __syncthreads();

@@ -14,7 +14,7 @@ for nb, B, M in ((32, 16384, 0), (33, 16384, 0), (48, 8192, 0), (64, 4096, 0), (
     rng = np.random.default_rng(nb)
     ctl = eb.ErgodicControl(eb.Omni(), 0.1, 5.0, 0.1, 1.0, nb, 1000, 100, R, umin, umax, batch=B)
     ctl.setTarget([eb.Gaussian([2.5, 2.5], [1.5, 1.5]), eb.Gaussian([8.5, 2.5], [1.5, 1.5])])
-    ctl.set_keep_ck(False)
+    ctl.keep_ck(False)
     x = np.column_stack([rng.uniform(0.5, 9.5, B), rng.uniform(0.5, 9.5, B), rng.uniform(-np.pi, np.pi, B)])
     ctl.set_ut(rng.uniform(umin, umax, size=(B, ctl.steps, 3)) * 0.5)
     for _ in range(M):
