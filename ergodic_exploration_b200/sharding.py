@@ -191,6 +191,10 @@ class PeerGather:
         """the publication branch eb_control_dev_gather takes for this controller's batch"""
         return gather_mode_for_batch(self.ctl.batch)
 
+    def fused(self) -> bool:
+        """True when a batch of this controller's size publishes from inside the solve kernel"""
+        return bool(self._lib.eb_peer_group_fused(self._h, int(self.ctl.batch)))
+
     @property
     def steps(self) -> int:
         return int(self._lib.eb_peer_group_steps(self._h))
