@@ -14,9 +14,9 @@ def row(r):
         name, r.get("n_gpus"), r.get("scaling"), r.get("value", float("nan")), r.get("unit", ""), r.get("ms_per_step", float("nan")),
         ("%.3f" % ro["frac"]) if ro.get("frac") is not None else None, e.get("value", float("nan")), e.get("ms_per_step", float("nan")),
         c.get("sm_mhz"), c.get("samples"), c.get("reasons"), (r.get("cpu_baseline") or {}).get("value")))
-    if "pipelined_gather" in r:
-        pg = r["pipelined_gather"]
-        print("    pipelined gather: value %.4g  ms/step %.4f" % (pg["value"], pg["ms_per_step"]))
+    if "strict_barrier" in r:
+        pg = r["strict_barrier"]
+        print("    strict per-step barrier: value %.4g  ms/step %.4f" % (pg["value"], pg["ms_per_step"]))
     for k in ("error", "parity"):
         if k in r:
             print("   ", k, r[k])
