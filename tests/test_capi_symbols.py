@@ -65,6 +65,11 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.eb_create(C.byref(cfg), C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
     cfg.num_basis, cfg.model = 10, 7
     assert lib.eb_create(C.byref(cfg), C.byref(h)) == capi.EB_ERR_INVALID_ARGUMENT
+    import torch
+    if not torch.cuda.is_available():
+        # 33..128 pass validation (the CTA-per-instance kernel): without a device the answer is "no device", not "bad argument"
+        cfg.num_basis, cfg.model = 64, capi.MODEL_OMNI
+        assert lib.eb_create(C.byref(cfg), C.byref(h)) == capi.EB_ERR_NO_DEVICE
     assert h.value is None
     assert lib.eb_control_host(None, 0, 1, 0, 1, None, None, None, None) == capi.EB_ERR_INVALID_ARGUMENT
     # round-2 entry points
