@@ -116,6 +116,9 @@ struct eb_phik_plan
   const eb::PhikTmaPeer* peer = nullptr;       // set for the duration of eb_phik_execute_allreduce_dev
   int max_parts = 0;
   long long launches = 0;
+  // nb > 32 on large grids: the 32-order TMA tile kernel once per (by, bx) block of orders; per-block tables
+  std::vector<double*> w_cxt, w_cxtf, w_cy;  // [nblk]: C_x re-laid (unfolded / folded), C_y [ny][32]
+  double* d_wraw = nullptr;                  // [nblk][nblk][1024] raw blocks
 };
 
 extern "C" {
@@ -225,8 +228,8 @@ eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin
   EB_CUDA_P(cudaMalloc(&p->d_cy, sizeof(double) * (size_t)ny * ld));
   EB_CUDA_P(cudaMalloc(&p->d_T, sizeof(double) * (size_t)ny * ld));
   // per-CTA blocks + the per-group sums of the TMA kernel's two-level final sum (wide: the one ld x ld raw block)
-  EB_CUDA_P(cudaMalloc(&p->d_parts, wide ? sizeof(double) * (size_t)ld * ld :
-                                           sizeof(double) * 1024 * (size_t)(p->max_parts + eb::kPtMaxGroups)));
+  EB_CUDA_P(cudaMalloc(&p->d_parts, std::max(sizeof(double) * (size_t)ld * ld,
+                                             sizeof(double) * 1024 * (size_t)(p->max_parts + eb::kPtMaxGroups))));
   EB_CUDA_P(cudaMalloc(&p->d_phik, sizeof(double) * (size_t)std::max(1024, nb * nb)));
   EB_CUDA_P(cudaMalloc(&p->d_sum, sizeof(double)));
   EB_CUDA_P(cudaMalloc(&p->d_done, sizeof(unsigned int) * (1 + eb::kPtMaxGroups)));
@@ -234,9 +237,56 @@ eb_status eb_phik_plan_create_ex(int device, int nx, int ny_total, int row_begin
   EB_CUDA_P(cudaMemcpy(p->d_xs, xs.data(), sizeof(double) * nx, cudaMemcpyHostToDevice));
   EB_CUDA_P(cudaMemcpy(p->d_ys, ys.data(), sizeof(double) * ny, cudaMemcpyHostToDevice));
   // basis.cpp:85: cos(k * (PI / l) * x)
-  eb::cos_table_kernel<<<(unsigned)(((size_t)nx * ld + 255) / 256), 256>>>(p->d_xs, nx, eb::kPi / lx, nb, ld, p->d_cx);
-  eb::cos_table_kernel<<<(unsigned)(((size_t)ny * ld + 255) / 256), 256>>>(p->d_ys, ny, eb::kPi / ly, nb, ld, p->d_cy);
+  eb::cos_table_kernel<<<(unsigned)(((size_t)nx * ld + 255) / 256), 256>>>(p->d_xs, nx, eb::kPi / lx, nb, ld, 0, p->d_cx);
+  eb::cos_table_kernel<<<(unsigned)(((size_t)ny * ld + 255) / 256), 256>>>(p->d_ys, ny, eb::kPi / ly, nb, ld, 0, p->d_cy);
   p->launches += 2;
+  if (wide && (long long)nx * ny >= (1 << 18) && eb::phik_tma_supported(nx, ny) && eb::phik_tma_encoder())
+  {
+    // large grid: the 32-order TMA tile kernel runs once per (by, bx) block of orders -- tables per block of 32 orders
+    const int nblk = ld / 32;
+    if (eb::phik_fold_shape_ok(nx))
+    {
+      double dev = 0.0;  // symmetry of the table on THIS grid over all nb orders (as below for nb <= 32)
+      for (int j = 0; j < nx / 2; j++)
+        for (int k = 0; k < nb; k++)
+        {
+          const double f = (double)k * (eb::kPi / lx);
+          const double a = std::cos(f * xs[j]), b = std::cos(f * xs[nx - 1 - j]);
+          dev = std::max(dev, std::fabs(a - ((k & 1) ? -b : b)));
+        }
+      p->fold_dev = dev;
+      p->fold = dev <= kFoldTol;
+    }
+    double* d_tmp = nullptr;  // one block of C_x, [nx][32]
+    EB_CUDA_P(cudaMalloc(&d_tmp, sizeof(double) * (size_t)nx * 32));
+    EB_CUDA_P(cudaMalloc(&p->d_wraw, sizeof(double) * 1024 * (size_t)nblk * nblk));
+    const int rows_u = eb::phik_tma_cx_rows(nx, false), rows_f = eb::phik_tma_cx_rows(nx / 2, true);
+    cudaError_t we = cudaSuccess;
+    for (int b = 0; b < nblk && we == cudaSuccess; b++)
+    {
+      double *cxt = nullptr, *cxtf = nullptr, *cyb = nullptr;
+      eb::cos_table_kernel<<<(unsigned)(((size_t)nx * 32 + 255) / 256), 256>>>(p->d_xs, nx, eb::kPi / lx, nb, 32, 32 * b, d_tmp);
+      we = cudaMalloc(&cxt, sizeof(double) * (size_t)rows_u * eb::kPdPitch);
+      p->w_cxt.push_back(cxt);
+      if (we == cudaSuccess)
+        eb::phik_tma_permute_cx<<<(rows_u * eb::kPdPitch + 255) / 256, 256>>>(d_tmp, nx, rows_u, 0, cxt);
+      if (we == cudaSuccess && p->fold)
+      {
+        we = cudaMalloc(&cxtf, sizeof(double) * (size_t)rows_f * eb::kPdPitch);
+        if (we == cudaSuccess)
+          eb::phik_tma_permute_cx<<<(rows_f * eb::kPdPitch + 255) / 256, 256>>>(d_tmp, nx / 2, rows_f, 1, cxtf);
+      }
+      p->w_cxtf.push_back(cxtf);
+      if (we == cudaSuccess) we = cudaMalloc(&cyb, sizeof(double) * (size_t)ny * 32);
+      p->w_cy.push_back(cyb);
+      if (we == cudaSuccess)
+        eb::cos_table_kernel<<<(unsigned)(((size_t)ny * 32 + 255) / 256), 256>>>(p->d_ys, ny, eb::kPi / ly, nb, 32, 32 * b, cyb);
+      p->launches += 3 + (p->fold ? 1 : 0);
+    }
+    if (we == cudaSuccess) we = cudaDeviceSynchronize();
+    cudaFree(d_tmp);
+    EB_CUDA_P(we);
+  }
   if (!wide && eb::phik_dmma_supported(nx, ny))
   {
     // room for the last column span's padding chunks (span <= nchunks)
@@ -306,6 +356,10 @@ void eb_phik_plan_destroy(eb_phik_plan* p)
   cudaFree(p->d_sum);
   cudaFree(p->d_phi_stage);
   cudaFree(p->d_done);
+  for (double* q : p->w_cxt) cudaFree(q);
+  for (double* q : p->w_cxtf) cudaFree(q);
+  for (double* q : p->w_cy) cudaFree(q);
+  cudaFree(p->d_wraw);
   delete p;
 }
 
@@ -323,7 +377,8 @@ eb_status eb_phik_plan_set_algo(eb_phik_plan* p, int algo)
     return fail(EB_ERR_INVALID_ARGUMENT, "algo must be 0 (auto), 1 (simple), 2 / 3 (register-streamed DMMA tiles, with / without "
                                          "the mirror fold) or 4 / 5 (TMA-staged DMMA tiles, with / without the mirror fold)");
   if (algo >= 2 && p->nb > 32)
-    return fail(EB_ERR_UNSUPPORTED, "the DMMA tile kernels contract 32 x 32 coefficient blocks: num_basis > 32 runs the simple pair (algo 0 / 1)");
+    return fail(EB_ERR_UNSUPPORTED, "num_basis > 32: algo 0 (auto: the TMA tile kernel per block of 32 x 32 orders on large grids, "
+                                    "else the simple pair) or 1 (simple pair)");
   if ((algo == 2 || algo == 3) && !eb::phik_dmma_supported(p->nx, p->ny))
     return fail(EB_ERR_UNSUPPORTED, "the register-streamed DMMA phi_k kernel needs nx % 4 == 0 and nx >= 128");
   if (algo >= 4 && (!eb::phik_tma_supported(p->nx, p->ny) || !eb::phik_tma_encoder()))
@@ -363,6 +418,26 @@ static eb_status phik_execute(eb_phik_plan* p, const double* phi_dev, double* ph
   EB_TRACE("eb_phik_execute");
   EB_CUDA(cudaSetDevice(p->device));
   int algo = p->algo;
+  if (p->nb > 32 && p->d_wraw && algo != 1 && (reinterpret_cast<uintptr_t>(phi_dev) & 15) == 0)
+  {
+    // wide route on a large grid: the TMA tile kernel once per (by, bx) block of 32 x 32 orders (raw blocks), then
+    // the assembly + normalisation
+    const int ld = p->ld, nblk = ld / 32;
+    for (int by = 0; by < nblk; by++)
+      for (int bx = 0; bx < nblk; bx++)
+      {
+        const int nbm = std::min(32, p->nb - 32 * std::min(by, bx));  // orders present in the wider of the two blocks
+        const eb::PhikTmaOut out{ p->d_done, nbm, nullptr, nullptr, p->d_wraw + 1024 * ((size_t)by * nblk + bx), nullptr };
+        const int np = eb::phik_tma_launch(phi_dev, p->nx, p->ny, p->fold ? p->w_cxtf[bx] : p->w_cxt[bx], p->w_cy[by],
+                                           p->d_parts, p->max_parts, p->fold, out, p->stream);
+        if (np < 0) return fail(EB_ERR_CUDA, std::string("phik_tma_launch (wide): ") + cudaGetErrorString(cudaGetLastError()));
+        p->launches += 1;
+      }
+    eb::phik_assemble_wide<<<(ld * ld + 255) / 256, 256, 0, p->stream>>>(p->d_wraw, p->nb, nblk, ld, phik_dev, phi_sum_dev, raw_dev);
+    p->launches += 1;
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+  }
   if (p->nb > 32)
   {
     // wide route: the simple pair over blocks of 32 orders, then the normalisation

@@ -21,13 +21,13 @@ namespace eb
 constexpr int kPhikLd = 32;  // leading dimension of the cosine tables / T for nb <= 32 (bases padded to 32)
 __host__ __device__ inline int phik_ld(int nb) { return nb <= 32 ? kPhikLd : ((nb + 31) & ~31); }
 
-// tab[j][k] = cos(k * (PI / l) * coord[j]) for k < nb, else 0 (basis.cpp:85)
-__global__ void cos_table_kernel(const double* __restrict__ coord, int n, double freq, int nb, int ld,
+// tab[j][k] = cos((k0 + k) * (PI / l) * coord[j]) for k0 + k < nb, else 0 (basis.cpp:85); k0: first order of the table
+__global__ void cos_table_kernel(const double* __restrict__ coord, int n, double freq, int nb, int ld, int k0,
                                  double* __restrict__ tab)
 {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n * ld) return;
-  const int j = (int)(idx / ld), k = (int)(idx % ld);
+  const int j = (int)(idx / ld), k = k0 + (int)(idx % ld);
   tab[idx] = k < nb ? cos((double)k * freq * coord[j]) : 0.0;
 }
 
@@ -122,6 +122,21 @@ __global__ void __launch_bounds__(1024) phik_finalize(const double* __restrict__
   const int kx = fold ? (col < 16 ? 2 * col : 2 * (col - 16) + 1) : col;
   if (raw) raw[ky * 32 + kx] = (ky < nb && kx < nb) ? s : 0.0;
   if (phik && ky < nb && kx < nb) phik[ky * nb + kx] = s / total;
+  if (t == 0 && phi_sum) *phi_sum = total;
+}
+
+// nb > 32 through the 32-order tile kernels: blocks[by][bx][ky][kx] (1024 doubles each) -> phik / raw (ld x ld)
+__global__ void phik_assemble_wide(const double* __restrict__ blocks, int nb, int nblk, int ld, double* __restrict__ phik,
+                                   double* __restrict__ phi_sum, double* __restrict__ raw)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ld * ld) return;
+  const double total = blocks[0];
+  const int ky = t / ld, kx = t % ld;
+  const bool in = ky < nb && kx < nb;
+  const double v = in ? blocks[((size_t)(ky >> 5) * nblk + (kx >> 5)) * 1024 + (ky & 31) * 32 + (kx & 31)] : 0.0;
+  if (raw) raw[t] = v;
+  if (phik && in) phik[ky * nb + kx] = v / total;
   if (t == 0 && phi_sum) *phi_sum = total;
 }
 

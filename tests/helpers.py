@@ -89,3 +89,21 @@ def assert_angle_close(a, b, what="", rtol=RTOL):
     d = np.asarray(a) - np.asarray(b)
     d = np.abs(np.arctan2(np.sin(d), np.cos(d)))
     assert d.max() <= 10 * rtol, f"{what}: max angular error {d.max():.3e}"
+
+
+def oracle_phik_threaded(phi, res, lx, ly, nb, threads=None):
+    """Oracle.phik_from_grid's arithmetic (the restated spatialCoeff, every cell x every basis function) with the rows
+    spread over the host cores: eo_phik_rows per row block (ctypes releases the GIL), partials summed in block order.
+    For the large-grid / wide-basis cases, where the single-threaded call takes minutes."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    ny = phi.shape[0]
+    total = float(phi.sum())
+    threads = threads or min(32, os.cpu_count() or 1)
+    bounds = np.linspace(0, ny, threads + 1).astype(int)
+    blocks = [(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    with ThreadPoolExecutor(len(blocks)) as ex:
+        parts = list(ex.map(lambda ab: Oracle.phik_rows(phi[ab[0]:ab[1]], ab[0], res, lx, ly, nb, total), blocks))
+    return np.sum(parts, axis=0), total

@@ -24,6 +24,27 @@ def centre_phik(density, res, nb):
     return Oracle.spatial_coeff(lx, ly, nb, vals, grid)
 
 
+@pytest.mark.parametrize("nx,ny", [(96, 80), (640, 512)])
+def test_map_target_wide_basis(nx, ny):
+    """num_basis > 32: entropy density kernel + the wide phi_k routes (simple pair on the small grid, the TMA tile kernel
+    per block of 32 x 32 orders on the large one)"""
+    import ergodic_exploration_b200 as eb
+
+    nb = 40
+    rng = np.random.default_rng(nx)
+    cells = rng.integers(-1, 101, size=(ny, nx)).astype(np.int8)
+    mt = eb.MapTarget(nx, ny, 0.05, nb)
+    got = mt.execute(cells)
+    dens = Oracle.entropy_grid(cells)
+    # eo_phik_rows takes accumulated sample points from 0: compare through the plain plan at the cell centres instead
+    plan = eb.PhikPlan(nx, ny, 0.05, mt.lx, mt.ly, nb, x_first=0.025, y_first=0.025, algo=1)
+    import torch
+    simple = plan.execute(torch.from_numpy(dens).cuda()).cpu().numpy()
+    assert_coeff_close(got, simple, f"map target nb=40 {nx}x{ny} vs the simple pair on the oracle's density")
+    if nx * ny <= 10000:
+        assert_coeff_close(got, centre_phik(dens, 0.05, nb), "map target nb=40 vs the oracle")
+
+
 def test_entropy_density_matches_reference_golden():
     import torch
 

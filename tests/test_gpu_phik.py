@@ -3,7 +3,7 @@ GPU against the CPU oracle.  Coefficient tolerance: max|a-b|/max|b| <= 1e-9."""
 import numpy as np
 import pytest
 
-from helpers import assert_coeff_close
+from helpers import assert_coeff_close, oracle_phik_threaded
 from oracle.pyoracle import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -41,7 +41,10 @@ def gaussian_mixture(rng, nx, ny, res, ng=8):
     (101, 101, 33, 0),    # num_basis > 32: the simple pair over blocks of 32 orders
     (160, 90, 64, 1),
     (77, 130, 100, 0),
-    (640, 512, 48, 0),    # a grid the tile kernels would take at nb <= 32
+    (640, 512, 48, 0),    # large grid: the TMA tile kernel once per block of 32 x 32 orders (mirror-folded)
+    (640, 512, 48, 1),    # ... and the simple pair on the same grid
+    (1026, 300, 64, 0),   # 2 x 2 full blocks, nx / 2 odd
+    (528, 500, 100, 0),   # 4 x 4 blocks, last one 4 orders wide
 ])
 def test_phik_matches_oracle(nx, ny, nb, algo):
     from ergodic_exploration_b200 import PhikPlan
@@ -52,7 +55,7 @@ def test_phik_matches_oracle(nx, ny, nb, algo):
     lx, ly = max(lx, res), max(ly, res)
     plan = PhikPlan(nx, ny, res, lx, ly, nb, algo=algo)
     got = plan.execute(phi)
-    want, total = Oracle.phik_from_grid(phi, res, lx, ly, nb)
+    want, total = (oracle_phik_threaded if nx * ny * nb * nb > 2e8 else Oracle.phik_from_grid)(phi, res, lx, ly, nb)
     assert_coeff_close(got, want, f"phi_k {nx}x{ny} nb={nb}")
     assert abs(plan.last_sum - total) <= 1e-9 * abs(total)
     assert abs(got[0] - 1.0) < 1e-12  # phi_0 == 1 after normalisation
@@ -138,6 +141,18 @@ def test_phik_wide_raw_block_and_tile_algos_refused():
     with pytest.raises(ErgodicB200Error) as e:
         PhikPlan(nx, ny, res, lx, ly, nb, algo=4)
     assert e.value.status == capi.EB_ERR_UNSUPPORTED
+    # the same through the per-block TMA route (large grid): raw blocks assembled into the ld x ld layout
+    nx, ny = 1024, 512
+    phi = rng.random((ny, nx))
+    lx, ly = (nx - 1) * res, (ny - 1) * res
+    plan = PhikPlan(nx, ny, res, lx, ly, nb)
+    raw = torch.full((64, 64), np.nan, dtype=torch.float64, device="cuda")
+    plan.execute_raw(torch.from_numpy(phi).cuda(), raw=raw)
+    raw = raw.cpu().numpy()
+    want, total = oracle_phik_threaded(phi, res, lx, ly, nb)
+    assert_coeff_close(raw[:nb, :nb].ravel() / raw[0, 0], want, "raw blocks nb=40, TMA route")
+    assert np.all(raw[nb:, :] == 0.0) and np.all(raw[:, nb:] == 0.0)
+    assert plan.launch_count() >= 5  # 4 tile-kernel launches + the assembly
 
 
 def test_plan_rejects_bad_arguments():
