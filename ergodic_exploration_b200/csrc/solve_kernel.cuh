@@ -439,6 +439,18 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
   const int inst = blockIdx.x * WARPS + warp;
   __shared__ WideIo<WARPS> wio;
   grid_dependency_wait();  // programmatic dependent launch: nothing global is touched before the previous kernel is complete
+#ifndef EB_NO_EARLY_UT
+  // the first round's controls do not depend on the pose: their HBM latency runs under the pose staging (which may be a
+  // PCIe round trip on the zero-copy host path) instead of behind it
+  double e_u0 = 0.0, e_u1 = 0.0, e_u2 = 0.0;
+  if (inst < p.B && lane + 1 < p.N)
+  {
+    const double* e_in = p.ut_in + ((size_t)inst * p.N + lane + 1) * 3;
+    e_u0 = e_in[0];
+    e_u1 = e_in[1];
+    e_u2 = e_in[2];
+  }
+#endif
   if constexpr (WideIo<WARPS>::kOn) wide_io_load(wio, p);
   if (inst >= p.B) return;
 #if EB_ABL & 128
@@ -517,6 +529,15 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
     const int i = r * 32 + lane;
     const bool valid = i < p.N;
     double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+#ifndef EB_NO_EARLY_UT
+    if (r == 0)
+    {
+      u0 = e_u0;
+      u1 = e_u1;
+      u2 = e_u2;
+    }
+    else
+#endif
     if (i + 1 < p.N)
     {  // shift left by one column, last column zero
       u0 = ut_in[(i + 1) * 3 + 0];
@@ -626,6 +647,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
     const bool valid = i < p.N;
     const double ce = rec[0 * npad + i], se = rec[1 * npad + i];
     const double xf = rec[2 * npad + i], yf = rec[3 * npad + i];
+#ifndef EB_NO_EARLY_BWD
+    double u0 = 0.0, u1 = 0.0;  // issued ahead of the gradient: their L2 latency runs under it (C2: 22.55 -> 22.42 us)
+    if (i + 1 < p.N)
+    {
+      u0 = ut_in[(i + 1) * 3 + 0];
+      u1 = ut_in[(i + 1) * 3 + 1];
+    }
+#endif
     double ca, sa, cb, sb;
     if (Cfg::kRecompute)
     {
@@ -812,12 +841,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
     }
 #endif
 
+#ifdef EB_NO_EARLY_BWD
     double u0 = 0.0, u1 = 0.0;
     if (i + 1 < p.N)
     {
       u0 = ut_in[(i + 1) * 3 + 0];
       u1 = ut_in[(i + 1) * 3 + 1];
     }
+#endif
     // gradBarrier :454-474
     double bx = 0.0, byv = 0.0;
     bx += 2.0 * (double)(xf > p.lx - p.beps) * (xf - (p.lx - p.beps));
