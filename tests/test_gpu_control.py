@@ -329,6 +329,48 @@ def test_wide_basis_persistent_ctas_and_sampled_memory(monkeypatch):
     assert_abs_rel_close(metric, ometric, "nb=36 device sampler metric")
 
 
+def test_wide_basis_host_paths_clone_and_faults():
+    """num_basis > 32 through the rest of the API: zero-copy host buffers == pageable buffers == device tensors (bit for
+    bit), optTraj from the pose the kernel recorded, a deep clone, c_k switched off, SimpleCart's lateral-velocity fault"""
+    import torch
+
+    from ergodic_exploration_b200 import ErgodicB200Error
+
+    rng = np.random.default_rng(64)
+    B, nb, model = 6, 40, MODEL_OMNI
+    ut = warm_ut(rng, B, 50, model)
+    a, b, c = make_gpu(model, B, nb=nb), make_gpu(model, B, nb=nb), make_gpu(model, B, nb=nb)
+    for g in (a, b, c):
+        g.set_ut(ut)
+    c.keep_ck(False)
+    x = random_states(rng, B)
+    xh = torch.empty((B, 3), dtype=torch.float64).pin_memory()
+    uh = torch.empty((B, 3), dtype=torch.float64).pin_memory()
+    xh.numpy()[:] = x
+    ua = a.control(BOUNDS_10, xh.numpy(), u0=uh.numpy()).copy()  # zero-copy
+    ub = b.control(BOUNDS_10, x.copy())                           # pageable
+    uc = c.control(BOUNDS_10, torch.from_numpy(x).cuda()).cpu().numpy()  # device tensors, no c_k dump
+    c.check()
+    np.testing.assert_array_equal(ua, ub)
+    np.testing.assert_array_equal(ua, uc)
+    np.testing.assert_array_equal(a.optTraj(), b.optTraj())
+    o = make_oracle(model, nb=nb)
+    o.set_ut(ut[2])
+    assert_abs_rel_close(ua[2], o.control(BOUNDS_10, x[2]), "wide row 2")
+    oxt = o.opt_traj()
+    assert_abs_rel_close(a.optTraj()[2][:, :2], oxt[:, :2], "optTraj xy row 2")
+    assert_angle_close(a.optTraj()[2][:, 2], oxt[:, 2], "optTraj theta row 2")
+    d = a.clone()
+    x2 = plant(x, ua)
+    np.testing.assert_array_equal(a.control(BOUNDS_10, x2), d.control(BOUNDS_10, x2))
+    cart = make_gpu(MODEL_SIMPLE_CART, 2, nb=nb)
+    bad = np.zeros((2, cart.steps, 3))
+    bad[1, 3, 1] = 0.25  # cart.hpp:167-170
+    cart.set_ut(bad)
+    with pytest.raises(ValueError, match="y-velocity"):
+        cart.control(BOUNDS_10, random_states(rng, 2))
+
+
 def test_long_horizon_many_rounds():
     """200 horizon steps = 7 rounds of 32 time-step lanes"""
     rng = np.random.default_rng(77)
