@@ -462,6 +462,7 @@ def bench_solve(ctx, key, steps, warmup, with_cpu=True):
         with ctx.clocks.region(key):
             torch.cuda._sleep(int(min(steps, 400) * 15e-6 * 1.9e9))
             step_dev(n_rot - 1)  # untimed, lines the ranks up on the device
+            launches0 = launch_total()  # `value` is this run at N > 1: gpu_launches counts its launches
             pa.record()
             for i in range(steps):
                 pg.control(BOUNDS, xd, metric=metd, ctl=ctls[i % n_rot])
@@ -469,6 +470,7 @@ def bench_solve(ctx, key, steps, warmup, with_cpu=True):
             pb.record()
             torch.cuda.synchronize()
         ctx.barrier()
+        launches = launch_total() - launches0
         for c_ in ctls:
             c_.check()
         pipe_ms = pa.elapsed_time(pb)
