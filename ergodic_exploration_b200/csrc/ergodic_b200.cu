@@ -543,6 +543,11 @@ struct eb_controller
   int cur = 0;                             // d_ut[cur] is ut_
   double* d_pose = nullptr;                // [B][3], pose_ of the last control()
   double* d_hist = nullptr;                // replay buffer [cap][B][3]
+  // Fourier-frame cosines of the stored states [cap][B][2] (what the solve kernels need from the buffer): rows
+  // [0, cos_count) are valid for the frame cos_key = {xmin, ymin, 1 / lx, 1 / ly}; brought up to date before a launch
+  double* d_hist_cos = nullptr;
+  long long cos_count = 0;
+  double cos_key[4] = { 0.0, 0.0, 0.0, 0.0 };
   long long hist_cap = 0, mem_count = 0;
   double *d_phik = nullptr, *d_lamk = nullptr;
   double *d_u0 = nullptr, *d_metric = nullptr, *d_ck = nullptr, *d_x = nullptr;
@@ -586,6 +591,16 @@ inline int zero_copy_max_batch()
   static const int v = [] {
     const char* e = std::getenv("EB_ZEROCOPY_MAX_BATCH");
     return e ? std::atoi(e) : 16384;
+  }();
+  return v;
+}
+
+// EB_REPLAY_COS=0: the solve kernels derive the replay states' cosines themselves (no cached rows), for A/B runs
+inline bool replay_cos_cache()
+{
+  static const bool v = [] {
+    const char* e = std::getenv("EB_REPLAY_COS");
+    return !e || std::atoi(e) != 0;
   }();
   return v;
 }
@@ -792,7 +807,7 @@ eb_status ensure_hist(eb_controller* c, long long need)
     // means cudaMalloc + copy + cudaFree in the middle of a control loop (and a re-mapping on every peer when the
     // context has peer access enabled)
     size_t free_b = 0, total_b = 0;
-    const size_t full = sizeof(double) * 3 * (size_t)c->B * (size_t)c->cfg.buffer_size;
+    const size_t full = sizeof(double) * (replay_cos_cache() ? 5 : 3) * (size_t)c->B * (size_t)c->cfg.buffer_size;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && full <= free_b / 8) cap = std::max<long long>(cap, c->cfg.buffer_size);
   }
   cap = std::min<long long>(cap, std::max<long long>((long long)c->cfg.buffer_size, need));
@@ -805,6 +820,36 @@ eb_status ensure_hist(eb_controller* c, long long need)
   cudaFree(c->d_hist);
   c->d_hist = nh;
   c->hist_cap = cap;
+  if (replay_cos_cache())
+  {
+    cudaFree(c->d_hist_cos);  // re-derived from the rows on the next control() (cos_count = 0)
+    c->d_hist_cos = nullptr;
+    c->cos_count = 0;
+    EB_CUDA(cudaMalloc(&c->d_hist_cos, sizeof(double) * 2 * (size_t)c->B * (size_t)cap));
+  }
+  return EB_OK;
+}
+
+// the cosine rows of every stored state, valid for the current Fourier frame (map origin and extent)
+eb_status ensure_hist_cos(eb_controller* c)
+{
+  if (!c->d_hist_cos || c->mem_count == 0) return EB_OK;
+  const double key[4] = { c->map_pos[0], c->map_pos[1], 1.0 / c->lx, 1.0 / c->ly };
+  if (std::memcmp(key, c->cos_key, sizeof(key)) != 0)
+  {
+    std::memcpy(c->cos_key, key, sizeof(key));
+    c->cos_count = 0;  // the frame moved (map growth, new origin): every row is re-derived
+  }
+  if (c->cos_count < c->mem_count)
+  {
+    const long long n = (c->mem_count - c->cos_count) * (long long)c->B;
+    const size_t off = (size_t)c->cos_count * (size_t)c->B;
+    eb::hist_cos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_hist + 3 * off, c->d_hist_cos + 2 * off, n,
+                                                                            key[0], key[1], key[2], key[3]);
+    EB_CUDA(cudaGetLastError());
+    c->launches += 1;
+    c->cos_count = c->mem_count;
+  }
   return EB_OK;
 }
 
@@ -922,6 +967,7 @@ void eb_destroy(eb_controller* c)
   cudaFree(c->d_ut[1]);
   cudaFree(c->d_pose);
   cudaFree(c->d_hist);
+  cudaFree(c->d_hist_cos);
   cudaFree(c->d_phik);
   cudaFree(c->d_lamk);
   cudaFree(c->d_u0);
@@ -1120,8 +1166,21 @@ static eb_status add_state_memory(eb_controller* c, const double* x, cudaMemcpyK
   EB_CUDA(cudaSetDevice(c->cfg.device));
   eb_status st = ensure_hist(c, c->mem_count + 1);
   if (st != EB_OK) return st;
-  EB_CUDA(cudaMemcpyAsync(c->d_hist + 3 * (size_t)c->B * (size_t)c->mem_count, x, sizeof(double) * 3 * c->B, kind,
-                          c->stream));
+  const size_t row = (size_t)c->B * (size_t)c->mem_count;
+  const double key[4] = { c->map_pos[0], c->map_pos[1], 1.0 / c->lx, 1.0 / c->ly };
+  if (kind == cudaMemcpyDeviceToDevice && c->d_hist_cos && c->cos_count == c->mem_count && c->lx > 0.0 && c->ly > 0.0 &&
+      std::memcmp(key, c->cos_key, sizeof(key)) == 0)
+  {
+    // the cosine rows are up to date for the current frame: the new row and its cosines in ONE launch
+    eb::add_state_kernel<<<(c->B + 255) / 256, 256, 0, c->stream>>>(x, c->d_hist + 3 * row, c->d_hist_cos + 2 * row, c->B,
+                                                                    key[0], key[1], key[2], key[3]);
+    EB_CUDA(cudaGetLastError());
+    c->launches += 1;
+    c->cos_count++;
+    c->mem_count++;
+    return EB_OK;
+  }
+  EB_CUDA(cudaMemcpyAsync(c->d_hist + 3 * row, x, sizeof(double) * 3 * c->B, kind, c->stream));
   if (kind == cudaMemcpyHostToDevice) EB_CUDA(cudaStreamSynchronize(c->stream));
   c->mem_count++;
   return EB_OK;
@@ -1199,6 +1258,12 @@ eb_status eb_control_dev(eb_controller* c, double xmin, double xmax, double ymin
   p.ut_in = c->d_ut[c->cur];
   p.ut_out = c->d_ut[c->cur ^ 1];
   p.hist = c->d_hist;
+  if (p.M > 0 && c->d_hist_cos && c->nb <= 32)
+  {  // (the CTA-per-instance kernel starts its tables at arbitrary orders and needs the coordinates themselves)
+    const eb_status hs = ensure_hist_cos(c);
+    if (hs != EB_OK) return hs;
+    p.hist_cos = c->d_hist_cos;
+  }
   p.mem_idx = mem_idx_dev;
   p.mem_idx_out = c->d_mem_idx_out;
   p.phik = c->d_phik;

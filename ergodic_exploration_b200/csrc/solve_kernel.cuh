@@ -116,6 +116,8 @@ struct SolveParams
   const double* ut_in;   // [B][N][3]
   double* ut_out;        // [B][N][3]
   const double* hist;    // [cap][B][3]
+  const double* hist_cos;  // [cap][B][2] or null: cos(pi (x - xmin) / lx), cos(pi (y - ymin) / ly) of every stored state,
+                           // kept by the host side for the current Fourier frame (hist_cos_kernel)
   const int* mem_idx;    // [B][batch_size]
   int* mem_idx_out;      // [B][batch_size]
   const double* phik;    // [nb*nb]
@@ -497,10 +499,19 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
         idx = 0;
       }
       if (p.idx_mode != 0 && p.mem_idx_out) p.mem_idx_out[(size_t)inst * p.batch_size + j] = (int)idx;
-      const double* h = p.hist + ((size_t)idx * p.B + inst) * 3;
-      const double xf = h[0] - p.xmin, yf = h[1] - p.ymin;
-      c1x = fast_cospi(xf * p.inv_lx);
-      c1y = fast_cospi(yf * p.inv_ly);
+      if (p.hist_cos)
+      {  // cosines cached per stored state: 16 bytes in, no trig
+        const double2 hc = *reinterpret_cast<const double2*>(p.hist_cos + ((size_t)idx * p.B + inst) * 2);
+        c1x = hc.x;
+        c1y = hc.y;
+      }
+      else
+      {
+        const double* h = p.hist + ((size_t)idx * p.B + inst) * 3;
+        const double xf = h[0] - p.xmin, yf = h[1] - p.ymin;
+        c1x = fast_cospi(xf * p.inv_lx);
+        c1y = fast_cospi(yf * p.inv_ly);
+      }
     }
     const int nvalid = min(32, p.M - base);
     coeff_chunk<NB>(tabx, lane, valid, nvalid, c1x, c1y, acc);
@@ -932,6 +943,34 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? SolveCfg<NB
     g_phase[inst * kPhaseSlots + 15] = smid;
   }
 #endif
+}
+
+// Fourier-frame cosines of stored states [first, first + n) x B: what the solve kernels need from the replay buffer
+// (ergodic_control.hpp:243-244 + basis.cpp:85 at k = 1; the higher orders follow by recurrence).  Same arithmetic as the
+// kernels' own path, so cached and uncached runs agree bit for bit.
+__global__ void __launch_bounds__(256) hist_cos_kernel(const double* __restrict__ hist, double* __restrict__ out, long long n,
+                                                       double xmin, double ymin, double inv_lx, double inv_ly)
+{
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double xf = hist[3 * e + 0] - xmin, yf = hist[3 * e + 1] - ymin;
+  out[2 * e + 0] = fast_cospi(xf * inv_lx);
+  out[2 * e + 1] = fast_cospi(yf * inv_ly);
+}
+// addStateMemory with the cache up to date: the new row and its cosines in one launch (instead of a copy + a launch)
+__global__ void __launch_bounds__(256) add_state_kernel(const double* __restrict__ x, double* __restrict__ hist_row,
+                                                        double* __restrict__ cos_row, int B, double xmin, double ymin,
+                                                        double inv_lx, double inv_ly)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const double a = x[3 * i + 0], b = x[3 * i + 1], c = x[3 * i + 2];
+  hist_row[3 * i + 0] = a;
+  hist_row[3 * i + 1] = b;
+  hist_row[3 * i + 2] = c;
+  const double xf = a - xmin, yf = b - ymin;
+  cos_row[2 * i + 0] = fast_cospi(xf * inv_lx);
+  cos_row[2 * i + 1] = fast_cospi(yf * inv_ly);
 }
 
 // optTraj() (ergodic_control.hpp:314-317): forward rollout of the CURRENT

@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? Solve2Cfg<N
         idx = 0;
       }
       if (p.idx_mode != 0 && p.mem_idx_out && axis == 0) p.mem_idx_out[(size_t)inst * p.batch_size + j] = (int)idx;
+      if (p.hist_cos) return __ldg(p.hist_cos + ((size_t)idx * p.B + inst) * 2 + axis);  // the cached cosine itself
       return __ldg(p.hist + ((size_t)idx * p.B + inst) * 3 + axis);
     };
     double cur = fetch(0);
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kSolveWarps ? Solve2Cfg<N
     {
       const double nxt = base + kTabSlots < p.M ? fetch(base + kTabSlots) : 0.0;
       const bool ok = base + slot < p.M;
-      const double c1 = fast_cospi((cur - origin) * inv_l);
+      const double c1 = p.hist_cos ? cur : fast_cospi((cur - origin) * inv_l);
       coeff_half<NB>(tab, lane, ok, p.M - base, c1, acc);
       cur = nxt;
     }
