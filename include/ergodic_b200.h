@@ -121,7 +121,10 @@ eb_status eb_set_phik(eb_controller *c, const double *phik, double lx, double ly
 eb_status eb_get_phik(const eb_controller *c, double *phik, double *lx, double *ly);
 
 /* ---- replay memory (addStateMemory :345-348, buffer.cpp:54-62) ---------- */
-/* x: 3 x B.  Silently dropped when buffer_size states are stored. */
+/* x: 3 x B.  Silently dropped when buffer_size states are stored.
+ * Next to the stored rows the library keeps 16 bytes per state and instance with the two Fourier-frame cosines the
+ * solve kernels need from a sampled state (re-derived when the map origin / extent changes; results are bit-identical
+ * with or without it; environment EB_REPLAY_COS=0 switches it off). */
 /* room for `count` stored states up front (capped at buffer_size): keeps allocations out of the control loop */
 eb_status eb_reserve_state_memory(eb_controller *c, long long count);
 eb_status eb_add_state_memory_host(eb_controller *c, const double *x);
